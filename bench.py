@@ -1,0 +1,308 @@
+#!/usr/bin/env python
+"""Benchmark of the hot path: matrix-free H|psi> (K1) on the BASELINE.json workloads.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+
+A step is one H|psi> over the whole state.  N = 1: synthetic molecular-type Hamiltonian,
+28 qubits (BASELINE.json configs[3]); N > 1: Fermi-Hubbard 4x4 (32 qubits, configs[4]) with
+the state sharded by its high qubits, launched under torchrun (one rank per GPU).
+Prints ONE JSON line (rank 0).  metric = term*amplitude updates/s = T * 2^n * K / time.
+`--impl reference` times the CPU restatement of the reference's own path (oracle/, numpy,
+term groups in worker processes like ParallelLinearQubitOperator) on a bounded sample.
+"""
+import argparse
+import ctypes
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = 'H|psi> term-amplitude updates/s'
+UNIT = 'term*amp/s'
+
+
+def measured_peak():
+    path = os.path.join(ROOT, 'MEASURED_PEAKS.json')
+    if os.path.exists(path):
+        try:
+            return float(json.load(open(path))['hbm_gbs']), 'measured (MEASURED_PEAKS.json hbm_gbs)'
+        except Exception:
+            pass
+    return 6650.0, 'fallback (B200_PROFILING.md 6.65 TB/s)'
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled during the timed region."""
+    QUERY = ('clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,'
+             'clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,'
+             'clocks_event_reasons.sw_power_cap')
+
+    def __init__(self, index=0):
+        self.index = index
+        self.proc = None
+        self.lines = []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ['nvidia-smi', '-i', str(self.index), '--query-gpu=' + self.QUERY,
+                 '--format=csv,noheader,nounits', '-lms', '200'],
+                stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._pump, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if not self.proc:
+            return {'sm_mhz': None, 'sm_max_mhz': None, 'reasons': ['nvidia-smi unavailable']}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        sm, smax, reasons = [], [], set()
+        names = ['hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap']
+        for line in self.lines:
+            parts = [p.strip() for p in line.split(',')]
+            if len(parts) < 7:
+                continue
+            try:
+                sm.append(float(parts[0]))
+                smax.append(float(parts[1]))
+            except ValueError:
+                continue
+            for name, flag in zip(names, parts[3:7]):
+                if flag.lower().startswith('active'):
+                    reasons.add(name)
+        return {'sm_mhz': float(numpy.median(sm)) if sm else None,
+                'sm_max_mhz': max(smax) if smax else None, 'samples': len(sm),
+                'reasons': sorted(reasons)}
+
+
+def workload_single(qubits):
+    from openfermion_b200 import models
+    if qubits % 2:
+        raise SystemExit('--qubits must be even (spin orbitals)')
+    op = models.molecular_jw(qubits // 2, seed=1234)
+    name = 'synthetic molecular-type JW Hamiltonian, %d qubits (random_interaction_operator(%d, expand_spin, seed=1234))' % (qubits, qubits // 2)
+    return op, name
+
+
+def cpu_baseline_sample(op, n, seconds_budget=30.0):
+    """Numpy port of the reference matvec (1 thread, like LinearQubitOperator) on a bounded
+    sample: the first few terms of the same table on the same-size state."""
+    sys.path.insert(0, os.path.join(ROOT, 'oracle'))
+    import pauli_oracle
+    try:
+        import psutil
+        avail = psutil.virtual_memory().available
+    except Exception:
+        avail = 64 << 30
+    n_cpu = n
+    while (1 << n_cpu) * 16 * 8 > avail and n_cpu > 16:
+        n_cpu -= 2
+    items = [(k, v) for k, v in op.terms.items() if k and all(q < n_cpu for q, _ in k)]
+    rng = numpy.random.default_rng(0)
+    vec = rng.normal(size=1 << n_cpu) + 1j * rng.normal(size=1 << n_cpu)
+    done, elapsed = 0, 0.0
+    per_term = None
+    while done < len(items):
+        take = 1 if per_term is None else max(1, min(8, int((seconds_budget - elapsed) / per_term)))
+        if per_term is not None and elapsed + per_term > seconds_budget:
+            break
+        chunk = dict(items[done:done + take])
+        t0 = time.perf_counter()
+        pauli_oracle.matvec(chunk, n_cpu, vec)
+        dt = time.perf_counter() - t0
+        elapsed += dt
+        done += len(chunk)
+        per_term = elapsed / done
+    value = done * float(1 << n_cpu) / elapsed
+    return {'value': value, 'unit': UNIT, 'cores': 1, 'kind': 'port',
+            'sample': '%d terms of the workload table on a 2^%d state, numpy port of '
+                      'LinearQubitOperator._matvec (oracle/pauli_oracle.py), %.1f s' % (done, n_cpu, elapsed)}
+
+
+def run_reference(args):
+    """Reference arm: CPU restatement with term groups in worker processes
+    (ParallelLinearQubitOperator semantics), bounded sample per step."""
+    rank = int(os.environ.get('RANK', '0'))
+    if rank != 0:
+        return
+    sys.path.insert(0, os.path.join(ROOT, 'oracle'))
+    import pauli_oracle
+    from openfermion_b200 import models
+    if args.gpus == 1:
+        op, name = workload_single(args.qubits)
+    else:
+        op, name = models.hubbard_jw(4, 4), 'Fermi-Hubbard 4x4 spinful JW, 32 qubits'
+    n = op.n_qubits
+    try:
+        import psutil
+        avail = psutil.virtual_memory().available
+    except Exception:
+        avail = 64 << 30
+    cores = len(os.sched_getaffinity(0)) if hasattr(os, 'sched_getaffinity') else (os.cpu_count() or 1)
+    n_cpu = n
+    procs = max(1, min(4, cores))
+    while (1 << n_cpu) * 16 * 8 * procs > avail and n_cpu > 16:
+        n_cpu -= 2
+    items = [(k, v) for k, v in op.terms.items() if k and all(q < n_cpu for q, _ in k)][:procs]
+    sample = dict(items)
+    rng = numpy.random.default_rng(0)
+    vec = rng.normal(size=1 << n_cpu) + 1j * rng.normal(size=1 << n_cpu)
+    for _ in range(args.warmup):
+        pauli_oracle.matvec_parallel(sample, n_cpu, vec, procs)
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        pauli_oracle.matvec_parallel(sample, n_cpu, vec, procs)
+    elapsed = time.perf_counter() - t0
+    value = len(sample) * float(1 << n_cpu) * args.steps / elapsed
+    desc = ('%d terms of the workload table per step on a 2^%d state, numpy port '
+            '(oracle/pauli_oracle.py matvec_parallel, %d worker processes)' % (len(sample), n_cpu, procs))
+    line = {
+        'impl': 'reference', 'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': args.gpus,
+        'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': 1e3 * elapsed / args.steps,
+        'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f64',
+        'data': 'synthetic', 'config': {'workload': name, 'sample': desc},
+        'cpu_baseline': {'value': value, 'unit': UNIT, 'cores': procs, 'kind': 'port', 'sample': desc},
+        'e2e': {'value': value, 'unit': UNIT, 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
+        'gpu_launches': 0,
+    }
+    print(json.dumps(line))
+
+
+def run_single(args):
+    from openfermion_b200 import _lib
+    from openfermion_b200.linalg import LinearQubitOperator
+    from openfermion_b200.linalg import krylov
+    _lib.require_device()
+    op, name = workload_single(args.qubits)
+    n = op.n_qubits
+    dim = 1 << n
+    lin = LinearQubitOperator(op, n)
+    plan = lin.plan
+    T, G = plan.n_terms, plan.n_groups
+    vp = ctypes.c_void_p
+
+    d_in = _lib.DeviceBuffer(dim * 16)
+    d_out = _lib.DeviceBuffer(dim * 16)
+    krylov.fill_random(dim, 42, False, d_in.ptr)
+    krylov.scal(dim, 1.0 / krylov.nrm2(dim, d_in.ptr), d_in.ptr)
+
+    ev = [vp() for _ in range(2)]
+    for e in ev:
+        _lib.call('ofb_event_create', ctypes.byref(e))
+
+    for _ in range(args.warmup):
+        plan.apply_device(d_in.ptr, d_out.ptr)
+    _lib.call('ofb_device_sync')
+    sampler = ClockSampler(0)
+    sampler.start()
+    time.sleep(0.25)
+    launches0 = _lib.launch_count()
+    _lib.call('ofb_event_record', ev[0], vp(None))
+    for _ in range(args.steps):
+        plan.apply_device(d_in.ptr, d_out.ptr)
+    _lib.call('ofb_event_record', ev[1], vp(None))
+    _lib.call('ofb_event_sync', ev[1])
+    _lib.call('ofb_device_sync')
+    launches = _lib.launch_count() - launches0
+    ms = ctypes.c_float()
+    _lib.call('ofb_event_elapsed_ms', ev[0], ev[1], ctypes.byref(ms))
+    clocks = sampler.stop()
+    seconds = ms.value / 1e3
+    value = T * float(dim) * args.steps / seconds
+
+    # sanity of the timed result: <v|Hv> through the vector kernels equals the fused K2 value
+    e_sep = krylov.dotc(dim, d_in.ptr, d_out.ptr)
+    e_fused = plan.expectation_device(d_in.ptr)
+    check = abs(e_sep - e_fused) / max(abs(e_fused), 1e-300)
+
+    # e2e: C-ABI call with pinned HOST buffers, H2D + kernel + D2H inside the timed region
+    h_in, h_out = vp(), vp()
+    _lib.call('ofb_host_alloc', ctypes.byref(h_in), ctypes.c_size_t(dim * 16))
+    _lib.call('ofb_host_alloc', ctypes.byref(h_out), ctypes.c_size_t(dim * 16))
+    _lib.call('ofb_memcpy_d2h', h_in, vp(d_in.ptr), ctypes.c_size_t(dim * 16), vp(None))
+    _lib.call('ofb_device_sync')
+    e2e_steps = max(1, min(args.steps, args.e2e_steps))
+    _lib.call('ofb_apply_host', plan.handle, h_in, h_out, 1)
+    t0 = time.perf_counter()
+    for _ in range(e2e_steps):
+        _lib.call('ofb_apply_host', plan.handle, h_in, h_out, 1)
+    e2e_seconds = time.perf_counter() - t0
+    e2e_value = T * float(dim) * e2e_steps / e2e_seconds
+    host_view = numpy.ctypeslib.as_array(ctypes.cast(h_out, ctypes.POINTER(ctypes.c_double)), (4,))
+    dev_head = krylov.download(2, d_out.ptr).view(numpy.float64)
+    assert numpy.array_equal(host_view, dev_head), 'e2e result differs from device-resident result'
+    _lib.call('ofb_host_free', h_in)
+    _lib.call('ofb_host_free', h_out)
+
+    peak, peak_src = measured_peak()
+    alg_bytes = 16.0 * dim * (G + 1)
+    achieved = alg_bytes / (seconds / args.steps) / 1e9
+    traffic = None
+    tpath = os.path.join(ROOT, 'profiles', 'k_apply_traffic.json')
+    if os.path.exists(tpath):
+        try:
+            rec = json.load(open(tpath))
+            if rec.get('n_qubits') == n:
+                traffic = rec.get('dram_bytes_per_launch')
+        except Exception:
+            pass
+    cpu = None if args.no_cpu_baseline else cpu_baseline_sample(op, n)
+    line = {
+        'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': 1, 'steps': args.steps,
+        'warmup': args.warmup, 'ms_per_step': ms.value / args.steps, 'higher_is_better': True,
+        'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f64', 'data': 'synthetic',
+        'config': {'workload': name, 'n_qubits': n, 'terms': T, 'x_groups': G,
+                   'l2_policy': 'inputs exceed L2 (state vector %.1f GB per buffer)' % (dim * 16 / 1e9),
+                   'timing': 'CUDA events on the launch stream', 'self_check_rel_err': check},
+        'clocks': clocks,
+        'e2e': {'value': e2e_value, 'unit': UNIT, 'h2d_bytes_per_step': dim * 16,
+                'd2h_bytes_per_step': dim * 16, 'steps': e2e_steps,
+                'path': 'ofb_apply_host (C ABI) with pinned host buffers'},
+        'gpu_launches': int(launches),
+        'roofline': {'bound': 'hbm', 'achieved': achieved, 'peak': peak, 'unit': 'GB/s',
+                     'frac': achieved / peak, 'traffic': traffic, 'peak_source': peak_src,
+                     'kernel': 'k_apply', 'algorithmic_bytes_per_launch': alg_bytes,
+                     'frac_of_8TBs_nominal': achieved / 8000.0},
+        'cpu_baseline': cpu,
+    }
+    print(json.dumps(line))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument('--gpus', type=int, default=1)
+    ap.add_argument('--steps', type=int, default=3)
+    ap.add_argument('--warmup', type=int, default=3)
+    ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
+    ap.add_argument('--qubits', type=int, default=28, help='N=1 workload size (even)')
+    ap.add_argument('--e2e-steps', type=int, default=2)
+    ap.add_argument('--no-cpu-baseline', action='store_true')
+    args = ap.parse_args()
+    if args.impl == 'reference':
+        return run_reference(args)
+    import __graft_entry__
+    __graft_entry__.build()
+    if args.gpus == 1 and int(os.environ.get('WORLD_SIZE', '1')) == 1:
+        return run_single(args)
+    from openfermion_b200 import distributed
+    return distributed.bench_main(args, METRIC, UNIT, ClockSampler, measured_peak)
+
+
+if __name__ == '__main__':
+    main()

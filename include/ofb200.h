@@ -1,0 +1,179 @@
+/* ofb200.h -- C ABI of the B200-native Pauli-sum Hamiltonian engine (libofb200.so).
+ *
+ * OpenFermion has no FFI; its boundary for this path is the Python API in
+ * openfermion/linalg/__init__.py:12-85.  Every entry point below is what a
+ * ctypes binding of that API calls; the comment above each one names the
+ * reference function (file:line under /root/reference/src/openfermion) whose
+ * arithmetic it replaces.  Conventions:
+ *   - plain pointers and sizes only, no C++/torch types;
+ *   - every function returns an int status (OFB_OK == 0); the message for the
+ *     last failure on the calling thread is ofb_last_error();
+ *   - "d_" pointers are device pointers on the plan's device, "h_" pointers are
+ *     host pointers owned by the caller; nothing allocated here is handed to
+ *     the caller except through ofb_malloc/ofb_host_alloc;
+ *   - `stream` is a cudaStream_t passed as void* (NULL = legacy default stream);
+ *   - amplitudes are complex128 stored (re, im) = 16 bytes; index bit (n-1-q)
+ *     is qubit q (linalg/linear_qubit_operator.py:78-84,126).
+ *   - there is no CPU fallback: without a CUDA device every compute call fails
+ *     with OFB_ERR_CUDA.
+ */
+#ifndef OFB200_H
+#define OFB200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define OFB_OK 0
+#define OFB_ERR_INVALID 1 /* bad argument */
+#define OFB_ERR_CUDA 2    /* CUDA runtime error (message has the cudaError string) */
+#define OFB_ERR_NOMEM 3   /* host or device allocation failed */
+#define OFB_ERR_STATE 4   /* call sequence error (e.g. csc_fill before csc_count) */
+
+typedef struct ofb_plan ofb_plan; /* compiled term tables on one device */
+
+/* ---- library / device ---------------------------------------------------- */
+int ofb_version(void);
+const char *ofb_last_error(void);
+int ofb_device_count(int *count);
+int ofb_set_device(int device);
+int ofb_device_info(int device, int *sm_count, size_t *total_bytes, size_t *free_bytes,
+                    int *cc_major, int *cc_minor);
+
+/* ---- memory / stream / event plumbing (so a ctypes host needs no torch) --- */
+int ofb_malloc(void **d_ptr, size_t bytes);
+int ofb_free(void *d_ptr);
+int ofb_host_alloc(void **h_ptr, size_t bytes); /* pinned */
+int ofb_host_free(void *h_ptr);
+int ofb_host_register(void *h_ptr, size_t bytes); /* pin caller memory in place */
+int ofb_host_unregister(void *h_ptr);
+int ofb_memcpy_h2d(void *d_dst, const void *h_src, size_t bytes, void *stream);
+int ofb_memcpy_d2h(void *h_dst, const void *d_src, size_t bytes, void *stream);
+int ofb_memcpy_d2d(void *d_dst, const void *d_src, size_t bytes, void *stream);
+int ofb_memset(void *d_ptr, int byte, size_t bytes, void *stream);
+int ofb_stream_create(void **stream);
+int ofb_stream_destroy(void *stream);
+int ofb_stream_sync(void *stream);
+int ofb_device_sync(void);
+int ofb_event_create(void **event);
+int ofb_event_destroy(void *event);
+int ofb_event_record(void *event, void *stream);
+int ofb_event_sync(void *event);
+int ofb_event_elapsed_ms(void *start, void *stop, float *ms);
+int ofb_stream_wait_event(void *stream, void *event);
+/* CUDA IPC, for peer shards of a state vector split over processes */
+int ofb_ipc_get_handle(void *d_ptr, void *handle64 /* 64 bytes out */);
+int ofb_ipc_open_handle(const void *handle64, void **d_ptr);
+int ofb_ipc_close_handle(void *d_ptr);
+int ofb_enable_peer_access(int peer_device);
+/* Number of kernels launched by this library in this process (bench's gpu_launches). */
+int64_t ofb_launch_count(void);
+
+/* ---- plans ----------------------------------------------------------------
+ * ofb_plan_create: compile a Pauli sum.  Term t is coeff[t] * P_t with P_t given
+ * by its masks exactly as LinearQubitOperator._matvec derives them
+ * (linalg/linear_qubit_operator.py:121-134): x_mask = X|Y positions, z_mask =
+ * Y|Z positions (so y_count = popc(x & z)).  coeff_ri holds (re, im) pairs of the
+ * reference coefficient (the i^y phase is applied inside).  Term order is kept
+ * inside each x-group (it is the summation order).  Replaces the per-call mask
+ * folding of linear_qubit_operator.py:107-148 and the per-term kron chain of
+ * linalg/sparse_tools.py:158-184. */
+int ofb_plan_create(int n_qubits, int64_t n_terms, const uint64_t *x_mask, const uint64_t *z_mask,
+                    const double *coeff_ri, int device, ofb_plan **plan);
+
+/* ofb_plan_create_projected: compile "projected" rows for the fermion route
+ * (linalg/sparse_tools.py:76-133, jordan_wigner_sparse): row t contributes
+ * H[c ^ x, c] += coeff * (-1)^popc(c & z) for every column c with
+ * (c & occ_mask) == occ_val.  Only the csc_* calls accept such a plan. */
+int ofb_plan_create_projected(int n_qubits, int64_t n_rows, const uint64_t *occ_mask,
+                              const uint64_t *occ_val, const uint64_t *x_mask,
+                              const uint64_t *z_mask, const double *coeff_ri, int device,
+                              ofb_plan **plan);
+int ofb_plan_destroy(ofb_plan *plan);
+/* n_qubits, T (terms kept), G (distinct x-masks), terms in the x==0 group, device */
+int ofb_plan_info(const ofb_plan *plan, int *n_qubits, int64_t *n_terms, int64_t *n_groups,
+                  int64_t *n_diag_terms, int *device);
+/* x-mask of group g in execution order, with its term count (host tables) */
+int ofb_plan_group(const ofb_plan *plan, int64_t g, uint64_t *x_mask, int64_t *n_terms);
+
+/* ---- K1: matrix-free H|psi>  (LinearQubitOperator._matvec,
+ * linalg/linear_qubit_operator.py:107-148; k columns = scipy _matmat as driven by
+ * linalg/davidson.py:249-256).  d_out[:, c] = H d_in[:, c]; columns are `ld`
+ * elements apart.  d_in and d_out must not alias. */
+int ofb_apply(ofb_plan *plan, const void *d_in, void *d_out, int ncols, int64_t ld, void *stream);
+
+/* Sharded / partial form used by the multi-GPU path and by fused Krylov steps:
+ *   out[j] (+)= sum over groups g in [g_begin, g_end) of
+ *             S_g(index_base | j) * in[j ^ (x_g & (2^local_bits - 1))]
+ * for j in [0, 2^local_bits).  The caller routes the high bits of x_g (which
+ * shard `d_in` is).  accumulate != 0 adds into d_out. */
+int ofb_apply_groups(ofb_plan *plan, const void *d_in, void *d_out, int local_bits,
+                     uint64_t index_base, int64_t g_begin, int64_t g_end, int accumulate,
+                     void *stream);
+
+/* Host-buffer convenience: H2D, ofb_apply, D2H (the call LinearQubitOperator.matvec makes).
+ * h_in/h_out are column-contiguous complex128 arrays of 2^n * ncols elements. */
+int ofb_apply_host(ofb_plan *plan, const void *h_in, void *h_out, int ncols);
+
+/* ---- K2: <psi|H|psi> without materialising H psi (expectation,
+ * linalg/sparse_tools.py:629-671: numpy.dot(conj(state), operator * state)). */
+int ofb_expectation(ofb_plan *plan, const void *d_state, double *h_out_ri /* 2 */, void *stream);
+int ofb_expectation_host(ofb_plan *plan, const void *h_state, double *h_out_ri);
+
+/* ---- K3: diagonal (get_linear_qubit_operator_diagonal,
+ * linalg/sparse_tools.py:197-247): float64[2^n], only x == 0 terms, real parts. */
+int ofb_diagonal(ofb_plan *plan, double *d_out, void *stream);
+int ofb_diagonal_host(ofb_plan *plan, double *h_out);
+
+/* ---- K4: CSC materialisation (qubit_operator_sparse linalg/sparse_tools.py:136-194,
+ * jordan_wigner_sparse :76-133; replaces scipy coo->csc + sum_duplicates +
+ * eliminate_zeros).  Two passes: count (also scans, result = nnz and the index
+ * width scipy would choose: 32 iff max(nnz, 2^n) < 2^31), then fill into caller
+ * buffers: indptr[2^n + 1], indices[nnz] (int32 or int64 per index_bits) and
+ * data[nnz] complex128; rows ascending inside each column, exact zeros dropped. */
+int ofb_csc_count(ofb_plan *plan, int64_t *nnz, int *index_bits, void *stream);
+int ofb_csc_fill(ofb_plan *plan, void *d_indptr, void *d_indices, void *d_data, int index_bits,
+                 void *stream);
+int ofb_csc_fill_host(ofb_plan *plan, void *h_indptr, void *h_indices, void *h_data,
+                      int index_bits);
+
+/* CSR/CSC-stored operator times vector for get_ground_state / SparseDavidson on an
+ * already materialised matrix (linalg/sparse_tools.py:578, linalg/davidson.py:369):
+ * y = A x with A in CSR (indptr[n_rows+1], indices, data complex128). */
+int ofb_csr_matvec(int64_t n_rows, const void *d_indptr, const void *d_indices, const void *d_data,
+                   int index_bits, const void *d_x, void *d_y, void *stream);
+
+/* ---- K5: vector kernels for the device-resident Krylov loops
+ * (numpy calls in linalg/davidson.py:257-339,439-469 and ARPACK internals behind
+ * linalg/sparse_tools.py:578).  All vectors complex128 of length n. Scalars that
+ * come back are written to host memory after a stream synchronise. */
+int ofb_vec_dotc(int64_t n, const void *d_x, const void *d_y, double *h_out_ri, void *stream);
+int ofb_vec_nrm2(int64_t n, const void *d_x, double *h_out, void *stream);
+int ofb_vec_maxabs(int64_t n, const void *d_x, double *h_out, void *stream);
+int ofb_vec_axpy(int64_t n, const double *alpha_ri, const void *d_x, void *d_y, void *stream);
+int ofb_vec_scal(int64_t n, const double *alpha_ri, void *d_x, void *stream);
+/* out[k] = conj(V[:,k]) . w for k < ncols (columns ld apart): V^H w in one pass over w */
+int ofb_vec_multi_dotc(int64_t n, int ncols, const void *d_V, int64_t ld, const void *d_w,
+                       double *h_out_ri /* 2*ncols */, void *stream);
+/* w = beta*w + sum_k a[k] V[:,k] */
+int ofb_vec_multi_axpy(int64_t n, int ncols, const double *a_ri /* 2*ncols */, const void *d_V,
+                       int64_t ld, const double *beta_ri, void *d_w, void *stream);
+/* Lanczos step tail: w -= alpha*v + beta*v_prev (alpha, beta real) */
+int ofb_vec_lanczos_update(int64_t n, double alpha, double beta, const void *d_v,
+                           const void *d_vprev, void *d_w, void *stream);
+/* Davidson correction (linalg/davidson.py:321-336): with dinv[j] = 1/(diag[j]-lambda) if
+ * |diag[j]-lambda| > eps else 1/eps, writes d_new = -r + v * (v^H dinv r)/(v^H dinv v). */
+int ofb_davidson_correction(int64_t n, const double *d_diag, double lambda, double eps,
+                            const void *d_r, const void *d_v, void *d_new, void *stream);
+/* real parts only (DavidsonOptions.real_only, linalg/davidson.py:183-184) */
+int ofb_vec_drop_imag(int64_t n, void *d_x, void *stream);
+/* deterministic pseudo-random fill in [0,1) (+ i[0,1) unless real_only), counter based */
+int ofb_vec_fill_random(int64_t n, uint64_t seed, int real_only, void *d_x, void *stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* OFB200_H */

@@ -1,0 +1,190 @@
+"""ctypes binding of libofb200.so (the C ABI declared in include/ofb200.h).
+
+There is no CPU fallback: if the shared library is missing, or a compute entry
+point is called on a machine without a CUDA device, the call raises.
+"""
+import ctypes
+import os
+
+import numpy
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, 'libofb200.so')
+
+c_void_p = ctypes.c_void_p
+c_int = ctypes.c_int
+c_int64 = ctypes.c_int64
+c_uint64 = ctypes.c_uint64
+c_size_t = ctypes.c_size_t
+c_double = ctypes.c_double
+P = ctypes.POINTER
+
+# name -> (restype, argtypes); must list every symbol of include/ofb200.h
+SIGNATURES = {
+    'ofb_version': (c_int, []),
+    'ofb_last_error': (ctypes.c_char_p, []),
+    'ofb_device_count': (c_int, [P(c_int)]),
+    'ofb_set_device': (c_int, [c_int]),
+    'ofb_device_info': (c_int, [c_int, P(c_int), P(c_size_t), P(c_size_t), P(c_int), P(c_int)]),
+    'ofb_malloc': (c_int, [P(c_void_p), c_size_t]),
+    'ofb_free': (c_int, [c_void_p]),
+    'ofb_host_alloc': (c_int, [P(c_void_p), c_size_t]),
+    'ofb_host_free': (c_int, [c_void_p]),
+    'ofb_host_register': (c_int, [c_void_p, c_size_t]),
+    'ofb_host_unregister': (c_int, [c_void_p]),
+    'ofb_memcpy_h2d': (c_int, [c_void_p, c_void_p, c_size_t, c_void_p]),
+    'ofb_memcpy_d2h': (c_int, [c_void_p, c_void_p, c_size_t, c_void_p]),
+    'ofb_memcpy_d2d': (c_int, [c_void_p, c_void_p, c_size_t, c_void_p]),
+    'ofb_memset': (c_int, [c_void_p, c_int, c_size_t, c_void_p]),
+    'ofb_stream_create': (c_int, [P(c_void_p)]),
+    'ofb_stream_destroy': (c_int, [c_void_p]),
+    'ofb_stream_sync': (c_int, [c_void_p]),
+    'ofb_device_sync': (c_int, []),
+    'ofb_event_create': (c_int, [P(c_void_p)]),
+    'ofb_event_destroy': (c_int, [c_void_p]),
+    'ofb_event_record': (c_int, [c_void_p, c_void_p]),
+    'ofb_event_sync': (c_int, [c_void_p]),
+    'ofb_event_elapsed_ms': (c_int, [c_void_p, c_void_p, P(ctypes.c_float)]),
+    'ofb_stream_wait_event': (c_int, [c_void_p, c_void_p]),
+    'ofb_ipc_get_handle': (c_int, [c_void_p, c_void_p]),
+    'ofb_ipc_open_handle': (c_int, [c_void_p, P(c_void_p)]),
+    'ofb_ipc_close_handle': (c_int, [c_void_p]),
+    'ofb_enable_peer_access': (c_int, [c_int]),
+    'ofb_launch_count': (c_int64, []),
+    'ofb_plan_create': (c_int, [c_int, c_int64, c_void_p, c_void_p, c_void_p, c_int, P(c_void_p)]),
+    'ofb_plan_create_projected': (c_int, [c_int, c_int64, c_void_p, c_void_p, c_void_p, c_void_p,
+                                          c_void_p, c_int, P(c_void_p)]),
+    'ofb_plan_destroy': (c_int, [c_void_p]),
+    'ofb_plan_info': (c_int, [c_void_p, P(c_int), P(c_int64), P(c_int64), P(c_int64), P(c_int)]),
+    'ofb_plan_group': (c_int, [c_void_p, c_int64, P(c_uint64), P(c_int64)]),
+    'ofb_apply': (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int64, c_void_p]),
+    'ofb_apply_groups': (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_uint64, c_int64, c_int64,
+                                 c_int, c_void_p]),
+    'ofb_apply_host': (c_int, [c_void_p, c_void_p, c_void_p, c_int]),
+    'ofb_expectation': (c_int, [c_void_p, c_void_p, P(c_double), c_void_p]),
+    'ofb_expectation_host': (c_int, [c_void_p, c_void_p, P(c_double)]),
+    'ofb_diagonal': (c_int, [c_void_p, c_void_p, c_void_p]),
+    'ofb_diagonal_host': (c_int, [c_void_p, c_void_p]),
+    'ofb_csc_count': (c_int, [c_void_p, P(c_int64), P(c_int), c_void_p]),
+    'ofb_csc_fill': (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_void_p]),
+    'ofb_csc_fill_host': (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int]),
+    'ofb_csr_matvec': (c_int, [c_int64, c_void_p, c_void_p, c_void_p, c_int, c_void_p, c_void_p,
+                               c_void_p]),
+    'ofb_vec_dotc': (c_int, [c_int64, c_void_p, c_void_p, P(c_double), c_void_p]),
+    'ofb_vec_nrm2': (c_int, [c_int64, c_void_p, P(c_double), c_void_p]),
+    'ofb_vec_maxabs': (c_int, [c_int64, c_void_p, P(c_double), c_void_p]),
+    'ofb_vec_axpy': (c_int, [c_int64, P(c_double), c_void_p, c_void_p, c_void_p]),
+    'ofb_vec_scal': (c_int, [c_int64, P(c_double), c_void_p, c_void_p]),
+    'ofb_vec_multi_dotc': (c_int, [c_int64, c_int, c_void_p, c_int64, c_void_p, P(c_double),
+                                   c_void_p]),
+    'ofb_vec_multi_axpy': (c_int, [c_int64, c_int, P(c_double), c_void_p, c_int64, P(c_double),
+                                   c_void_p, c_void_p]),
+    'ofb_vec_lanczos_update': (c_int, [c_int64, c_double, c_double, c_void_p, c_void_p, c_void_p,
+                                       c_void_p]),
+    'ofb_davidson_correction': (c_int, [c_int64, c_void_p, c_double, c_double, c_void_p, c_void_p,
+                                        c_void_p, c_void_p]),
+    'ofb_vec_drop_imag': (c_int, [c_int64, c_void_p, c_void_p]),
+    'ofb_vec_fill_random': (c_int, [c_int64, c_uint64, c_int, c_void_p, c_void_p]),
+}
+
+_NO_STATUS = {'ofb_version', 'ofb_last_error', 'ofb_launch_count'}
+
+
+class OfbError(RuntimeError):
+    """A libofb200 call failed (status != OFB_OK)."""
+
+
+_lib = None
+
+
+def load():
+    """Loads libofb200.so (once).  Raises if it has not been built."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise OfbError(
+            'libofb200.so is not built (%s); run `python -c "import __graft_entry__ as g; '
+            'g.build()"` -- there is no CPU fallback.' % LIB_PATH
+        )
+    lib = ctypes.CDLL(LIB_PATH)
+    for name, (restype, argtypes) in SIGNATURES.items():
+        fn = getattr(lib, name)
+        fn.restype = restype
+        fn.argtypes = argtypes
+    _lib = lib
+    return lib
+
+
+def call(name, *args):
+    """Calls an int-status entry point and raises OfbError with the library message."""
+    lib = load()
+    status = getattr(lib, name)(*args)
+    if status != 0:
+        raise OfbError('%s failed (%d): %s' % (name, status, lib.ofb_last_error().decode()))
+
+
+def launch_count():
+    return int(load().ofb_launch_count())
+
+
+def device_count():
+    n = c_int(0)
+    try:
+        call('ofb_device_count', ctypes.byref(n))
+    except OfbError:
+        return 0
+    return n.value
+
+
+def require_device():
+    if device_count() < 1:
+        raise OfbError('no CUDA device visible: openfermion_b200 has no CPU fallback')
+
+
+def ptr(array):
+    """Host pointer of a numpy array as c_void_p."""
+    return c_void_p(array.ctypes.data)
+
+
+class DeviceBuffer:
+    """A raw device allocation owned by Python (freed on garbage collection)."""
+
+    def __init__(self, nbytes):
+        self.nbytes = int(nbytes)
+        p = c_void_p()
+        call('ofb_malloc', ctypes.byref(p), c_size_t(max(self.nbytes, 1)))
+        self.ptr = p.value
+
+    def at(self, byte_offset):
+        return c_void_p(self.ptr + int(byte_offset))
+
+    def free(self):
+        if getattr(self, 'ptr', None):
+            try:
+                call('ofb_free', c_void_p(self.ptr))
+            finally:
+                self.ptr = None
+
+    def __del__(self):
+        try:
+            self.free()
+        except Exception:
+            pass
+
+
+def to_device(array, stream=None):
+    array = numpy.ascontiguousarray(array)
+    buf = DeviceBuffer(array.nbytes)
+    if array.nbytes:
+        call('ofb_memcpy_h2d', c_void_p(buf.ptr), ptr(array), c_size_t(array.nbytes), c_void_p(stream))
+        call('ofb_stream_sync', c_void_p(stream))
+    return buf
+
+
+def to_host(buf, shape, dtype, byte_offset=0, stream=None):
+    out = numpy.empty(shape, dtype=dtype)
+    if out.nbytes:
+        call('ofb_memcpy_d2h', ptr(out), buf.at(byte_offset), c_size_t(out.nbytes), c_void_p(stream))
+        call('ofb_stream_sync', c_void_p(stream))
+    return out

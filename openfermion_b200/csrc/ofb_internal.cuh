@@ -1,0 +1,107 @@
+// Internal declarations shared by the translation units of libofb200.so.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include <atomic>
+#include <string>
+#include <vector>
+
+#include "ofb200.h"
+
+namespace ofb {
+
+// ---- error plumbing --------------------------------------------------------
+void set_error(const std::string &msg);
+int fail(int code, const std::string &msg);
+int cuda_fail(cudaError_t e, const char *what, const char *file, int line);
+extern std::atomic<int64_t> g_launches;
+
+#define OFB_CUDA(call)                                                          \
+    do {                                                                        \
+        cudaError_t e__ = (call);                                               \
+        if (e__ != cudaSuccess) return ofb::cuda_fail(e__, #call, __FILE__, __LINE__); \
+    } while (0)
+
+#define OFB_LAUNCH_CHECK()                              \
+    do {                                                \
+        ofb::g_launches.fetch_add(1);                   \
+        OFB_CUDA(cudaGetLastError());                   \
+    } while (0)
+
+// ---- device tables ---------------------------------------------------------
+// One x-group of the gather form  out[j] += S_g(j) * in[j ^ x],
+// S_g(j) = sum_t c_t (-1)^popc(j & z_t)  (SURVEY.md section 0.4).
+enum GroupKind : uint32_t { KIND_COMPLEX = 0, KIND_REAL = 1, KIND_IMAG = 2 };
+struct __align__(16) GroupDesc {
+    uint64_t x;
+    uint32_t begin;  // first term
+    uint32_t count;  // bits 0..29 term count, bits 30..31 GroupKind
+};
+// Primary component of a term: real part (KIND_REAL / KIND_COMPLEX) or imaginary
+// part (KIND_IMAG) of c_t = coeff_t * (-i)^y_t, next to its z mask so that one
+// 128-bit uniform load fetches both.
+struct __align__(16) TermZC {
+    uint64_t z;
+    double c;
+};
+// Scatter-form row for CSC assembly: H[col ^ x, col] += c * (-1)^popc(col & z)
+// for columns with (col & occ_mask) == occ_val.  x lives in the group.
+struct __align__(16) ScatterRow {
+    uint64_t z;
+    uint64_t occ_mask;
+    uint64_t occ_val;
+    uint64_t pad;
+    double cr, ci;
+};
+
+}  // namespace ofb
+
+struct ofb_plan {
+    int n_qubits = 0;
+    int device = 0;
+    bool projected = false;  // fermion-route rows: only CSC calls are valid
+    int64_t n_terms = 0;
+    int64_t n_groups = 0;
+    int64_t n_diag_terms = 0;
+    bool z_fits32 = false;
+    // host copies (group order = ascending x)
+    std::vector<uint64_t> h_group_x;
+    std::vector<uint32_t> h_group_begin;  // n_groups + 1
+    std::vector<uint32_t> h_group_kind;
+    // device tables: gather form (apply / expectation / diagonal)
+    ofb::GroupDesc *d_groups = nullptr;
+    ofb::TermZC *d_zc = nullptr;
+    double *d_ci = nullptr;  // secondary component (imag part for KIND_COMPLEX)
+    // device tables: scatter form (CSC)
+    ofb::ScatterRow *d_rows = nullptr;
+    uint32_t *d_sib = nullptr;  // [n_groups][n_qubits] sibling-subtree sizes
+    // CSC state between count and fill
+    int64_t *d_colptr = nullptr;   // 2^n + 1 exclusive scan of counts
+    uint32_t *d_bitmap = nullptr;  // [words][2^n] rank-ordered non-zero flags
+    int64_t csc_nnz = -1;
+    int64_t bitmap_words = 0;
+    // scratch for reductions
+    double *d_partials = nullptr;
+    size_t partials_bytes = 0;
+    double *h_pinned_scalars = nullptr;  // 64 doubles
+    // staging for *_host calls
+    void *d_stage_in = nullptr;
+    void *d_stage_out = nullptr;
+    size_t stage_in_bytes = 0, stage_out_bytes = 0;
+};
+
+namespace ofb {
+int ensure_partials(ofb_plan *plan, size_t bytes);
+int ensure_stage(ofb_plan *plan, size_t in_bytes, size_t out_bytes);
+// launches implemented in apply.cu
+int launch_apply(ofb_plan *plan, const void *d_in, void *d_out, int local_bits, uint64_t index_base,
+                 int64_t g0, int64_t g1, int accumulate, cudaStream_t s);
+int launch_expectation(ofb_plan *plan, const void *d_state, double *h_out, cudaStream_t s);
+int launch_diagonal(ofb_plan *plan, double *d_out, cudaStream_t s);
+// shared reduction helper (vec.cu): sums `count` rows of `width` doubles
+int reduce_partials(const double *d_partials, int64_t count, int width, double *d_out,
+                    cudaStream_t s);
+double *global_scratch(size_t bytes);  // per-device growable scratch for vec kernels
+double *global_pinned();               // 4096 pinned doubles
+}  // namespace ofb

@@ -1,0 +1,29 @@
+"""Drop-in for the hot-path subset of `openfermion.linalg` (linalg/__init__.py:12-85)."""
+from openfermion_b200.linalg.linear_qubit_operator import (
+    LinearQubitOperator,
+    LinearQubitOperatorOptions,
+    ParallelLinearQubitOperator,
+    apply_operator,
+    generate_linear_qubit_operator,
+)
+from openfermion_b200.linalg.sparse_tools import (
+    expectation,
+    get_gap,
+    get_ground_state,
+    get_linear_qubit_operator_diagonal,
+    get_sparse_operator,
+    inner_product,
+    jordan_wigner_sparse,
+    qubit_operator_sparse,
+    variance,
+)
+from openfermion_b200.linalg.davidson import (
+    Davidson,
+    DavidsonError,
+    DavidsonOptions,
+    QubitDavidson,
+    SparseDavidson,
+    append_random_vectors,
+    generate_random_vectors,
+    orthonormalize,
+)

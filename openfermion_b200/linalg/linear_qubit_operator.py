@@ -1,0 +1,134 @@
+"""Drop-in `LinearQubitOperator` family backed by the sm_100a matrix-free kernel (K1).
+
+Mirrors /root/reference/src/openfermion/linalg/linear_qubit_operator.py: same class and
+function names, constructor arguments, attributes and error behaviour; `_matvec` runs
+`ofb_apply_host` instead of the per-term numpy loop (linear_qubit_operator.py:107-148).
+"""
+import os
+
+import numpy
+import scipy.sparse.linalg
+
+from openfermion_b200.compiler import compile_qubit_operator
+from openfermion_b200.ops import count_qubits
+from openfermion_b200.plan import PauliPlan
+
+
+def get_available_cpu_count():
+    """Usable CPU cores (reference config.py:29-55), honouring pytest-xdist's worker count."""
+    try:
+        cores = len(os.sched_getaffinity(0))
+    except AttributeError:
+        cores = os.cpu_count() or 1
+    workers = os.environ.get('PYTEST_XDIST_WORKER_COUNT')
+    if workers:
+        cores = max(1, cores // int(workers))
+    return cores
+
+
+class LinearQubitOperatorOptions:
+    """Options for ParallelLinearQubitOperator (linear_qubit_operator.py:38-71).
+
+    On the GPU path a term-group "worker" is an x-mask group of one compiled plan, so no
+    process pool is ever created: `pool` stays whatever the caller passed (None by default).
+    """
+
+    def __init__(self, processes=10, pool=None):
+        if processes <= 0:
+            raise ValueError('Invalid number of processors specified {} <= 0'.format(processes))
+        self.processes = min(processes, get_available_cpu_count())
+        self.pool = pool
+
+    def get_processes(self, num):
+        return max(min(num, self.processes), 1)
+
+    def get_pool(self, num=None):
+        raise NotImplementedError(
+            'openfermion_b200 applies all term groups inside one CUDA kernel; there is no '
+            'multiprocessing pool to hand out.'
+        )
+
+
+class LinearQubitOperator(scipy.sparse.linalg.LinearOperator):
+    """Matrix-free action of a QubitOperator on 2^n complex128 amplitudes.
+
+    Qubit q is index bit n_qubits-1-q (linear_qubit_operator.py:78-84).  The term table
+    is compiled into a device plan on first use; constructing the object needs no GPU.
+    """
+
+    def __init__(self, qubit_operator, n_qubits=None):
+        calculated_n_qubits = count_qubits(qubit_operator)
+        if n_qubits is None:
+            n_qubits = calculated_n_qubits
+        elif n_qubits < calculated_n_qubits:
+            raise ValueError(
+                'Invalid number of qubits specified '
+                '{} < {}.'.format(n_qubits, calculated_n_qubits)
+            )
+        n_hilbert = 2**n_qubits
+        super().__init__(shape=(n_hilbert, n_hilbert), dtype=complex)
+        self.qubit_operator = qubit_operator
+        self.n_qubits = n_qubits
+        self._plan = None
+
+    @property
+    def plan(self):
+        """The compiled device plan (built on first access; raises without a GPU)."""
+        if self._plan is None:
+            x, z, c = compile_qubit_operator(self.qubit_operator, self.n_qubits)
+            self._plan = PauliPlan(self.n_qubits, x, z, c)
+        return self._plan
+
+    def _matvec(self, x):
+        arr = numpy.asarray(x)
+        vec = numpy.ascontiguousarray(arr.reshape(-1), dtype=numpy.complex128)
+        return self.plan.apply_host(vec).reshape(arr.shape)
+
+    def _matmat(self, X):
+        X = numpy.asarray(X)
+        return self.plan.apply_host(numpy.asfortranarray(X, dtype=numpy.complex128))
+
+
+class ParallelLinearQubitOperator(scipy.sparse.linalg.LinearOperator):
+    """Same attributes as the reference's process-pool variant
+    (linear_qubit_operator.py:151-209): `qubit_operator_groups`, `linear_operators`,
+    `options`.  The sum over term groups is evaluated by one plan on the GPU."""
+
+    def __init__(self, qubit_operator, n_qubits=None, options=None):
+        n_qubits = n_qubits or count_qubits(qubit_operator)
+        n_hilbert = 2**n_qubits
+        super().__init__(shape=(n_hilbert, n_hilbert), dtype=complex)
+        self.qubit_operator = qubit_operator
+        self.n_qubits = n_qubits
+        self.options = options or LinearQubitOperatorOptions()
+        self.qubit_operator_groups = list(
+            qubit_operator.get_operator_groups(self.options.processes)
+        )
+        self.linear_operators = [
+            LinearQubitOperator(operator, n_qubits) for operator in self.qubit_operator_groups
+        ]
+        self._fused = LinearQubitOperator(qubit_operator, n_qubits)
+
+    def _matvec(self, x):
+        if not self.linear_operators:
+            return numpy.zeros(x.shape)
+        return self._fused._matvec(x)
+
+    def _matmat(self, X):
+        if not self.linear_operators:
+            return numpy.zeros(numpy.asarray(X).shape)
+        return self._fused._matmat(X)
+
+
+def apply_operator(args):
+    """Helper kept for API compatibility (linear_qubit_operator.py:212-215)."""
+    operator, vec = args
+    return operator * vec
+
+
+def generate_linear_qubit_operator(qubit_operator, n_qubits=None, options=None):
+    """LinearQubitOperator when options is None, else the parallel variant
+    (linear_qubit_operator.py:218-234)."""
+    if options is None:
+        return LinearQubitOperator(qubit_operator, n_qubits)
+    return ParallelLinearQubitOperator(qubit_operator, n_qubits, options)

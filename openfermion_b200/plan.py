@@ -1,0 +1,134 @@
+"""Python owner of an `ofb_plan` (compiled term tables on one GPU)."""
+import ctypes
+
+import numpy
+import scipy.sparse
+
+from openfermion_b200 import _lib
+from openfermion_b200._lib import c_void_p, c_int, c_int64
+
+
+class PauliPlan:
+    """Compiled Pauli sum: apply / expectation / diagonal / CSC through the C ABI."""
+
+    def __init__(self, n_qubits, x_mask, z_mask, coeff, device=0):
+        _lib.require_device()
+        self.n_qubits = int(n_qubits)
+        self.dim = 1 << self.n_qubits
+        x = numpy.ascontiguousarray(x_mask, dtype=numpy.uint64)
+        z = numpy.ascontiguousarray(z_mask, dtype=numpy.uint64)
+        c = numpy.ascontiguousarray(coeff, dtype=numpy.complex128)
+        if not (len(x) == len(z) == len(c)):
+            raise ValueError('term table arrays differ in length')
+        handle = c_void_p()
+        _lib.call('ofb_plan_create', c_int(self.n_qubits), c_int64(len(x)), _lib.ptr(x), _lib.ptr(z),
+                  _lib.ptr(c), c_int(device), ctypes.byref(handle))
+        self.handle = handle
+        self.device = device
+        self.projected = False
+        self._read_info()
+
+    @classmethod
+    def projected_rows(cls, n_qubits, occ_mask, occ_val, x_mask, z_mask, coeff, device=0):
+        """Fermion-route plan (jordan_wigner_sparse); only the CSC calls are valid."""
+        _lib.require_device()
+        self = cls.__new__(cls)
+        self.n_qubits = int(n_qubits)
+        self.dim = 1 << self.n_qubits
+        arrays = [numpy.ascontiguousarray(a, dtype=numpy.uint64)
+                  for a in (occ_mask, occ_val, x_mask, z_mask)]
+        c = numpy.ascontiguousarray(coeff, dtype=numpy.complex128)
+        handle = c_void_p()
+        _lib.call('ofb_plan_create_projected', c_int(self.n_qubits), c_int64(len(c)),
+                  *[_lib.ptr(a) for a in arrays], _lib.ptr(c), c_int(device), ctypes.byref(handle))
+        self.handle = handle
+        self.device = device
+        self.projected = True
+        self._read_info()
+        return self
+
+    def _read_info(self):
+        n = c_int()
+        t, g, d = c_int64(), c_int64(), c_int64()
+        dev = c_int()
+        _lib.call('ofb_plan_info', self.handle, ctypes.byref(n), ctypes.byref(t), ctypes.byref(g),
+                  ctypes.byref(d), ctypes.byref(dev))
+        self.n_terms, self.n_groups, self.n_diag_terms = t.value, g.value, d.value
+
+    def group(self, g):
+        x = ctypes.c_uint64()
+        count = c_int64()
+        _lib.call('ofb_plan_group', self.handle, c_int64(g), ctypes.byref(x), ctypes.byref(count))
+        return x.value, count.value
+
+    def group_x_masks(self):
+        return numpy.array([self.group(g)[0] for g in range(self.n_groups)], dtype=numpy.uint64)
+
+    # ---- host-buffer calls (the ones the drop-in API makes) -------------------
+    def apply_host(self, columns):
+        """columns: complex128, Fortran-contiguous (dim, k) or (dim,) -> same shape."""
+        cols = numpy.asarray(columns, dtype=numpy.complex128)
+        ncols = 1 if cols.ndim == 1 else cols.shape[1]
+        cols = numpy.asfortranarray(cols) if cols.ndim == 2 else numpy.ascontiguousarray(cols)
+        out = numpy.empty_like(cols, order='F' if cols.ndim == 2 else 'C')
+        _lib.call('ofb_apply_host', self.handle, _lib.ptr(cols), _lib.ptr(out), c_int(ncols))
+        return out
+
+    def expectation_host(self, state):
+        state = numpy.ascontiguousarray(state, dtype=numpy.complex128).reshape(-1)
+        out = (ctypes.c_double * 2)()
+        _lib.call('ofb_expectation_host', self.handle, _lib.ptr(state), out)
+        return complex(out[0], out[1])
+
+    def diagonal_host(self):
+        out = numpy.empty(self.dim, dtype=numpy.float64)
+        _lib.call('ofb_diagonal_host', self.handle, _lib.ptr(out))
+        return out
+
+    def csc_host(self):
+        """Materialises the operator as scipy CSC with scipy's own index-width rule."""
+        nnz = c_int64()
+        bits = c_int()
+        _lib.call('ofb_csc_count', self.handle, ctypes.byref(nnz), ctypes.byref(bits), c_void_p(None))
+        idx_dtype = numpy.int32 if bits.value == 32 else numpy.int64
+        indptr = numpy.empty(self.dim + 1, dtype=idx_dtype)
+        indices = numpy.empty(nnz.value, dtype=idx_dtype)
+        data = numpy.empty(nnz.value, dtype=numpy.complex128)
+        _lib.call('ofb_csc_fill_host', self.handle, _lib.ptr(indptr), _lib.ptr(indices),
+                  _lib.ptr(data), bits)
+        if nnz.value == 0:
+            # the reference's empty result is float64
+            return scipy.sparse.csc_matrix((self.dim, self.dim), dtype=numpy.float64)
+        mat = scipy.sparse.csc_matrix((data, indices, indptr), shape=(self.dim, self.dim))
+        mat.has_sorted_indices = True
+        return mat
+
+    # ---- device-pointer calls (Krylov loops, bench) ----------------------------
+    def apply_device(self, d_in, d_out, ncols=1, ld=None, stream=None):
+        _lib.call('ofb_apply', self.handle, c_void_p(d_in), c_void_p(d_out), c_int(ncols),
+                  c_int64(self.dim if ld is None else ld), c_void_p(stream))
+
+    def apply_groups_device(self, d_in, d_out, local_bits, index_base, g_begin, g_end, accumulate,
+                            stream=None):
+        _lib.call('ofb_apply_groups', self.handle, c_void_p(d_in), c_void_p(d_out), c_int(local_bits),
+                  ctypes.c_uint64(index_base), c_int64(g_begin), c_int64(g_end), c_int(accumulate),
+                  c_void_p(stream))
+
+    def expectation_device(self, d_state, stream=None):
+        out = (ctypes.c_double * 2)()
+        _lib.call('ofb_expectation', self.handle, c_void_p(d_state), out, c_void_p(stream))
+        return complex(out[0], out[1])
+
+    def diagonal_device(self, d_out, stream=None):
+        _lib.call('ofb_diagonal', self.handle, c_void_p(d_out), c_void_p(stream))
+
+    def close(self):
+        if getattr(self, 'handle', None):
+            _lib.call('ofb_plan_destroy', self.handle)
+            self.handle = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass

@@ -1,0 +1,181 @@
+"""TEST INFRASTRUCTURE -- generates tests/golden/*.npz from the REAL reference.
+
+Run in the build container only (needs /root/reference through oracle/ref_shim.py):
+    python oracle/make_golden.py
+Every case stores the operator (term strings + coefficients), the seeded inputs and the
+reference's own outputs, and asserts on the way that the oracle restatement
+(oracle/pauli_oracle.py) reproduces them, so the GPU box -- which has neither the
+reference nor this script's inputs -- can check both the oracle and the CUDA path.
+"""
+import hashlib
+import os
+import sys
+import zlib
+
+import numpy
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(HERE)
+sys.path.insert(0, HERE)
+sys.path.insert(0, ROOT)
+
+import ref_shim  # noqa: E402
+
+ref_shim.load()
+import pauli_oracle as po  # noqa: E402
+from openfermion.hamiltonians.hubbard import fermi_hubbard  # noqa: E402
+from openfermion.linalg import (LinearQubitOperator, get_ground_state,  # noqa: E402
+                                get_linear_qubit_operator_diagonal, get_sparse_operator,
+                                jordan_wigner_sparse, qubit_operator_sparse, expectation)
+from openfermion.ops.operators import QubitOperator  # noqa: E402
+from openfermion.ops.representations import InteractionOperator  # noqa: E402
+from openfermion.chem.molecular_data import spinorb_from_spatial  # noqa: E402
+from openfermion.testing.testing_utils import (random_interaction_operator,  # noqa: E402
+                                               random_qubit_operator)
+from openfermion.transforms.opconversions import (bravyi_kitaev, get_fermion_operator,  # noqa: E402
+                                                  jordan_wigner)
+
+GOLDEN = os.path.join(ROOT, 'tests', 'golden')
+LIH = '/root/reference/src/openfermion/testing/data/H1-Li1_sto-3g_singlet_1.45.hdf5'
+
+
+def qubit_term_str(term):
+    return ' '.join('{}{}'.format(a, q) for q, a in term)
+
+
+def fermion_term_str(term):
+    return ' '.join('{}{}'.format(q, '^' if a else '') for q, a in term)
+
+
+def pack_terms(terms, to_str):
+    strs = numpy.array([to_str(t) for t in terms], dtype=str)
+    coeffs = numpy.array([complex(c) for c in terms.values()], dtype=numpy.complex128)
+    is_complex = numpy.array([isinstance(c, (complex, numpy.complexfloating)) for c in terms.values()])
+    return strs, coeffs, is_complex
+
+
+def same_csc(a, b):
+    return (a.shape == b.shape and a.indices.dtype == b.indices.dtype
+            and numpy.array_equal(a.indptr, b.indptr) and numpy.array_equal(a.indices, b.indices)
+            and numpy.array_equal(a.data, b.data))
+
+
+def sha(a):
+    return hashlib.sha256(numpy.ascontiguousarray(a).tobytes()).hexdigest()
+
+
+def qubit_cases():
+    rng = numpy.random.default_rng(20261019)
+    cases = {}
+    ops = {}
+    for seed in range(8):
+        n = 3 + seed
+        ops['random_q%d_s%d' % (n, seed)] = (random_qubit_operator(n, 24, n, seed=seed), n)
+    ops['hubbard_2x2_jw'] = (jordan_wigner(fermi_hubbard(2, 2, 1.0, 4.0)), 8)
+    ops['hubbard_2x2_mu_h_jw'] = (jordan_wigner(fermi_hubbard(2, 2, 1.0, 4.0, 0.3, 0.2)), 8)
+    ops['hubbard_2x2_bk'] = (bravyi_kitaev(fermi_hubbard(2, 2, 1.0, 4.0)), 8)
+    ops['hubbard_2x3_jw'] = (jordan_wigner(fermi_hubbard(2, 3, 1.0, 4.0)), 12)
+    mol = random_interaction_operator(3, expand_spin=True, real=True, seed=5)
+    ops['molecular_6_jw'] = (jordan_wigner(mol), 6)
+    ops['molecular_6_bk'] = (bravyi_kitaev(get_fermion_operator(mol)), 6)
+    ops['molecular_8_jw'] = (jordan_wigner(random_interaction_operator(4, expand_spin=True, real=True, seed=1234)), 8)
+    cplx = random_interaction_operator(3, expand_spin=False, real=False, seed=11)
+    ops['molecular_3_complex_jw'] = (jordan_wigner(cplx), 3)
+    ops['padded_n7'] = (QubitOperator('X0 Y1 Z3', 0.5 - 0.25j) + QubitOperator('Z1 Z2', 1.5), 7)
+    ops['identity_only'] = (QubitOperator((), 2.5), 4)
+    names = []
+    for name, (op, n) in ops.items():
+        v = rng.normal(size=2**n) + 1j * rng.normal(size=2**n)
+        strs, coeffs, is_complex = pack_terms(op.terms, qubit_term_str)
+        ref_mv = LinearQubitOperator(op, n) * v
+        assert numpy.array_equal(ref_mv, po.matvec(op.terms, n, v)), name
+        ref_csc = qubit_operator_sparse(op, n)
+        assert same_csc(ref_csc, po.qubit_operator_sparse(op.terms, n)), name
+        ref_exp = expectation(LinearQubitOperator(op, n), v)
+        cases[name + '/terms'] = strs
+        cases[name + '/coeffs'] = coeffs
+        cases[name + '/coeff_is_complex'] = is_complex
+        cases[name + '/n_qubits'] = numpy.array(n)
+        cases[name + '/vec'] = v
+        cases[name + '/matvec'] = ref_mv
+        cases[name + '/expectation'] = numpy.array(ref_exp)
+        cases[name + '/indptr'] = ref_csc.indptr
+        cases[name + '/indices'] = ref_csc.indices
+        cases[name + '/data'] = ref_csc.data
+        if not is_complex.any():
+            ref_diag = get_linear_qubit_operator_diagonal(op, n)
+            assert numpy.array_equal(ref_diag, po.diagonal(op.terms, n)), name
+            cases[name + '/diagonal'] = ref_diag
+        names.append(name)
+    cases['names'] = numpy.array(names, dtype=str)
+    numpy.savez_compressed(os.path.join(GOLDEN, 'qubit_cases.npz'), **cases)
+    print('qubit_cases:', len(names), 'cases')
+
+
+def fermion_cases():
+    cases = {}
+    ops = {
+        'hubbard_2x2': (fermi_hubbard(2, 2, 1.0, 4.0), 8),
+        'hubbard_2x2_mu_h': (fermi_hubbard(2, 2, 1.0, 4.0, 0.3, 0.2), 8),
+        'hubbard_2x3_open': (fermi_hubbard(2, 3, 1.0, 2.0, periodic=False), 12),
+        'molecular_6': (get_fermion_operator(random_interaction_operator(3, expand_spin=True, real=True, seed=5)), 6),
+        'molecular_8_dense': (get_fermion_operator(random_interaction_operator(8, expand_spin=False, real=True, seed=3)), 8),
+        'molecular_4_complex': (get_fermion_operator(random_interaction_operator(4, expand_spin=False, real=False, seed=9)), 4),
+    }
+    names = []
+    for name, (op, n) in ops.items():
+        strs, coeffs, _ = pack_terms(op.terms, fermion_term_str)
+        ref_csc = jordan_wigner_sparse(op, n)
+        assert same_csc(ref_csc, po.jordan_wigner_sparse(op.terms, n)), name
+        cases[name + '/terms'] = strs
+        cases[name + '/coeffs'] = coeffs
+        cases[name + '/n_qubits'] = numpy.array(n)
+        cases[name + '/indptr'] = ref_csc.indptr
+        cases[name + '/indices'] = ref_csc.indices
+        cases[name + '/data'] = ref_csc.data
+        names.append(name)
+    cases['names'] = numpy.array(names, dtype=str)
+    numpy.savez_compressed(os.path.join(GOLDEN, 'fermion_cases.npz'), **cases)
+    print('fermion_cases:', len(names), 'cases')
+
+
+def lih_case():
+    """Config 1: LiH sto-3g from the bundled HDF5.  No h5py here: the two gzip-chunked
+    float64 datasets are read at their byte offsets (one_body_integrals 6x6 at 2775,
+    two_body_integrals 6^4 at 22704; SURVEY.md section 7 hard part 5) and validated by
+    reproducing the file's stored fci_energy through the reference."""
+    raw = open(LIH, 'rb').read()
+    one = numpy.frombuffer(zlib.decompressobj().decompress(raw[2775:]), dtype='<f8').reshape(6, 6).copy()
+    two = numpy.frombuffer(zlib.decompressobj().decompress(raw[22704:]), dtype='<f8').reshape(6, 6, 6, 6).copy()
+    nuclear_repulsion = 1.0948493970827586
+    fci_energy = -7.8809823148256966
+    hf_energy = -7.8625677857178955
+    one_so, two_so = spinorb_from_spatial(one, two)
+    ham = InteractionOperator(nuclear_repulsion, one_so, 0.5 * two_so)
+    csc = get_sparse_operator(ham)
+    e0, psi = get_ground_state(csc)
+    assert abs(e0 - fci_energy) < 1e-7, (e0, fci_energy)
+    assert same_csc(csc, po.jordan_wigner_sparse(get_fermion_operator(ham).terms, 12))
+    qham = jordan_wigner(ham)
+    hf_state = numpy.zeros(2**12)
+    hf_state[sum(2 ** (11 - i) for i in range(4))] = 1.0
+    e_hf = expectation(csc, hf_state)
+    assert abs(e_hf - hf_energy) < 1e-7
+    strs, coeffs, is_complex = pack_terms(qham.terms, qubit_term_str)
+    numpy.savez_compressed(
+        os.path.join(GOLDEN, 'lih_sto3g.npz'),
+        one_body_integrals=one, two_body_integrals=two, nuclear_repulsion=nuclear_repulsion,
+        fci_energy=fci_energy, hf_energy=hf_energy, reference_e0=e0, reference_hf_expectation=e_hf,
+        nnz=csc.nnz, indptr=csc.indptr, indices_sha256=sha(csc.indices), indices_dtype=str(csc.indices.dtype),
+        data_abs_sum=numpy.abs(csc.data).sum(), data_sum=csc.data.sum(),
+        data_head=csc.data[:512], indices_head=csc.indices[:512],
+        qubit_terms=strs, qubit_coeffs=coeffs, n_qubit_terms=len(strs),
+    )
+    print('lih: nnz', csc.nnz, 'E0', e0, 'T', len(strs))
+
+
+if __name__ == '__main__':
+    os.makedirs(GOLDEN, exist_ok=True)
+    qubit_cases()
+    fermion_cases()
+    lih_case()

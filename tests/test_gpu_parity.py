@@ -1,0 +1,297 @@
+"""GPU: parity of the CUDA path (through the Python mirror -> C ABI) against the oracle,
+the reference's known answers and the golden vectors generated from the real reference.
+Bars (BASELINE.json): CSC indptr/indices bit-exact; values, matvecs, expectations within
+1e-12 relative."""
+import hashlib
+
+import numpy
+import pytest
+import scipy.sparse
+
+import c_oracle
+import helpers
+import known_answers as ka
+import pauli_oracle as po
+from openfermion_b200 import compiler, models
+from openfermion_b200.linalg import (LinearQubitOperator, ParallelLinearQubitOperator,
+                                     LinearQubitOperatorOptions, expectation, variance,
+                                     get_linear_qubit_operator_diagonal, get_sparse_operator,
+                                     jordan_wigner_sparse, qubit_operator_sparse)
+from openfermion_b200.ops import QubitOperator, count_qubits
+
+pytestmark = pytest.mark.gpu
+RTOL = 1e-12
+
+
+# ---- reference known answers -----------------------------------------------------
+@pytest.mark.parametrize('name,op,n,vec,expected', ka.MATVEC, ids=[k[0] for k in ka.MATVEC])
+def test_matvec_known_answers(name, op, n, vec, expected):
+    got = LinearQubitOperator(op, n) * vec
+    assert got.dtype == numpy.complex128 and got.shape == vec.shape
+    assert numpy.allclose(got, expected, rtol=0, atol=1e-14)
+
+
+def test_matvec_wrong_length_raises():
+    with pytest.raises(ValueError):
+        LinearQubitOperator(QubitOperator('X3')) * numpy.zeros(4)
+
+
+def test_matvec_compare_with_sparse():
+    op = QubitOperator('X0 Y1 Z3')
+    mat = qubit_operator_sparse(op).toarray()
+    lin = LinearQubitOperator(op)
+    cols = numpy.array([lin * v for v in numpy.identity(16)]).T
+    assert numpy.array_equal(cols, mat)
+    assert numpy.array_equal(lin.matmat(numpy.identity(16, dtype=complex)), mat)
+
+
+@pytest.mark.parametrize('name,op,n,data,indices,shape', ka.CSC, ids=[k[0] for k in ka.CSC])
+def test_csc_known_answers(name, op, n, data, indices, shape):
+    mat = get_sparse_operator(op, n)
+    assert scipy.sparse.isspmatrix_csc(mat) and mat.shape == shape
+    assert list(mat.data) == data
+    assert list(mat.indices) == indices
+    ref = po.qubit_operator_sparse(op.terms, n)
+    assert mat.dtype == ref.dtype and mat.indices.dtype == ref.indices.dtype
+    assert numpy.array_equal(mat.indptr, ref.indptr)
+
+
+@pytest.mark.parametrize('name,op,n,expected', ka.DIAGONAL, ids=[k[0] for k in ka.DIAGONAL])
+def test_diagonal_known_answers(name, op, n, expected):
+    got = get_linear_qubit_operator_diagonal(op, n)
+    assert got.dtype == numpy.float64
+    assert numpy.array_equal(got, expected)
+
+
+@pytest.mark.parametrize('string', ['Z1 X2 Y5', 'Z1 Z2 Z5'])
+def test_diagonal_equals_operator_on_identity(string):
+    op = QubitOperator(string)
+    want = numpy.diag(LinearQubitOperator(op).matmat(numpy.eye(2**6, dtype=complex)))
+    assert numpy.allclose(get_linear_qubit_operator_diagonal(op), want)
+
+
+def test_diagonal_complex_coefficient_raises():
+    with pytest.raises(TypeError):
+        get_linear_qubit_operator_diagonal(QubitOperator('Z0', 1.0 + 0j))
+
+
+def test_expectation_known_answers():
+    # sparse_tools_test.py:607-637
+    vector = numpy.array([0.0, 1.0j, 0.0, 1.0j])
+    sparse = get_sparse_operator(QubitOperator('X0'), n_qubits=2)
+    assert abs(expectation(sparse, vector) - 2.0) < 1e-14
+    density = scipy.sparse.csc_matrix(numpy.outer(vector, numpy.conjugate(vector)))
+    assert abs(expectation(sparse, density) - 2.0) < 1e-14
+    lin = LinearQubitOperator(QubitOperator('X0'), n_qubits=2)
+    assert abs(expectation(lin, vector) - 2.0) < 1e-14
+    assert abs(expectation(sparse, vector.reshape(4, 1)) - 2.0) < 1e-14
+    assert abs(expectation(sparse, numpy.array([1j, -1j, -1j, -1j]))) < 1e-14
+    with pytest.raises(ValueError):
+        expectation(lin, scipy.sparse.csc_matrix(numpy.array([1, 0, 0, 0])))
+    with pytest.raises(ValueError):
+        expectation(scipy.sparse.csc_matrix(numpy.array([1, 0, 0, 0])), lin)
+
+
+def test_variance_known_answers():
+    # sparse_tools_test.py:640-671
+    X = get_sparse_operator(QubitOperator('X0'))
+    Z = get_sparse_operator(QubitOperator('Z0'))
+    zero, plus = numpy.array([1.0, 0.0]), numpy.array([1.0, 1.0]) / numpy.sqrt(2)
+    assert abs(variance(X, zero) - 1.0) < 1e-13 and abs(variance(Z, zero)) < 1e-13
+    assert abs(variance(Z, plus) - 1.0) < 1e-13 and abs(variance(X, plus)) < 1e-13
+    lin = LinearQubitOperator(QubitOperator('X0') + QubitOperator('Z0', 0.5))
+    mat = get_sparse_operator(QubitOperator('X0') + QubitOperator('Z0', 0.5))
+    v = numpy.array([0.6, 0.8j])
+    assert abs(variance(lin, v) - variance(mat, v)) < 1e-13
+
+
+# ---- golden vectors from the real reference ------------------------------------------
+@pytest.mark.parametrize('case', helpers.qubit_cases(), ids=lambda c: c.name)
+def test_golden_matvec_expectation_diagonal(case):
+    op = helpers.qubit_case_operator(case)
+    lin = LinearQubitOperator(op, case.n)
+    assert helpers.close(lin * case['vec'], case['matvec'], RTOL)
+    want = complex(case['expectation'])
+    scale = numpy.sum(numpy.abs(case['coeffs'])) * numpy.vdot(case['vec'], case['vec']).real
+    assert abs(expectation(lin, case['vec']) - want) <= RTOL * scale
+    if case.has('diagonal'):
+        assert helpers.close(get_linear_qubit_operator_diagonal(op, case.n), case['diagonal'], RTOL)
+
+
+@pytest.mark.parametrize('case', helpers.qubit_cases(), ids=lambda c: c.name)
+def test_golden_csc_pauli_route(case):
+    op = helpers.qubit_case_operator(case)
+    mat = qubit_operator_sparse(op, case.n)
+    helpers.assert_csc_matches(mat, case['indptr'], case['indices'], case['data'], RTOL)
+
+
+@pytest.mark.parametrize('case', helpers.fermion_cases(), ids=lambda c: c.name)
+def test_golden_csc_fermion_route(case):
+    op = helpers.fermion_operator_from(case['terms'], case['coeffs'])
+    mat = jordan_wigner_sparse(op, case.n)
+    helpers.assert_csc_matches(mat, case['indptr'], case['indices'], case['data'], RTOL)
+    assert mat.has_canonical_format
+
+
+def test_lih_sparse_operator_matches_reference():
+    data = helpers.golden('lih_sto3g.npz')
+    ham = models.molecular_hamiltonian(float(data['nuclear_repulsion']), data['one_body_integrals'],
+                                       data['two_body_integrals'])
+    mat = get_sparse_operator(ham)
+    assert mat.nnz == int(data['nnz']) and str(mat.indices.dtype) == str(data['indices_dtype'])
+    assert numpy.array_equal(mat.indptr, data['indptr'])
+    assert hashlib.sha256(mat.indices.tobytes()).hexdigest() == str(data['indices_sha256'])
+    assert numpy.array_equal(mat.indices[:512], data['indices_head'])
+    assert helpers.close(mat.data[:512], data['data_head'], RTOL)
+    assert abs(numpy.abs(mat.data).sum() - float(data['data_abs_sum'])) <= 1e-12 * float(data['data_abs_sum'])
+    hf_state = numpy.zeros(2**12)
+    hf_state[sum(2 ** (11 - i) for i in range(4))] = 1.0
+    assert abs(expectation(mat, hf_state) - complex(data['reference_hf_expectation'])) < 1e-12
+    qop = helpers.qubit_operator_from(data['qubit_terms'], data['qubit_coeffs'])
+    assert abs(expectation(LinearQubitOperator(qop, 12), hf_state + 0j)
+               - complex(data['reference_hf_expectation'])) < 1e-11
+
+
+# ---- larger sizes against the C oracle ---------------------------------------------------
+def _state(n, seed):
+    rng = numpy.random.default_rng(seed)
+    v = rng.normal(size=2**n) + 1j * rng.normal(size=2**n)
+    return v / numpy.linalg.norm(v)
+
+
+@pytest.mark.parametrize('name,builder', [
+    ('hubbard_2x4_n16', lambda: models.hubbard_jw(2, 4)),
+    ('hubbard_2x5_n20', lambda: models.hubbard_jw(2, 5)),
+    ('molecular_n12', lambda: models.molecular_jw(6, seed=1234)),
+    ('molecular_n16', lambda: models.molecular_jw(8, seed=1234)),
+    ('dense_paulis_complex_n15', lambda: models.random_pauli_sum(15, 300, 3, True)),
+    ('dense_paulis_real_n13', lambda: models.random_pauli_sum(13, 500, 4, False)),
+    ('hubbard_3x4_n24', lambda: models.hubbard_jw(3, 4)),
+])
+def test_matvec_and_expectation_vs_c_oracle(name, builder):
+    op = builder()
+    n = op.n_qubits
+    x, z, c = compiler.compile_qubit_operator(op, n)
+    v = _state(n, 7)
+    want = c_oracle.matvec(n, x, z, c, v)
+    lin = LinearQubitOperator(op, n)
+    got = lin * v
+    assert helpers.close(got, want, RTOL)
+    e_want = numpy.vdot(v, want)
+    assert abs(expectation(lin, v) - e_want) <= RTOL * numpy.sum(numpy.abs(c))
+    if not numpy.any(c.imag):
+        assert helpers.close(get_linear_qubit_operator_diagonal(op, n), c_oracle.diagonal(n, x, z, c), RTOL)
+
+
+def test_matvec_accepts_reference_input_kinds():
+    op = models.hubbard_jw(2, 2)
+    lin = LinearQubitOperator(op, 8)
+    ints = numpy.arange(256)
+    want = po.matvec(op.terms, 8, ints)
+    assert helpers.close(lin * ints, want, RTOL)
+    col = (ints * 0.5).reshape(256, 1)
+    out = lin * col
+    assert out.shape == (256, 1) and helpers.close(out[:, 0], want * 0.5, RTOL)
+    X = numpy.stack([_state(8, s) for s in range(5)], axis=1)
+    assert helpers.close(lin.matmat(X), po.matmat(op.terms, 8, X), RTOL)
+    assert helpers.close(lin @ X, po.matmat(op.terms, 8, X), RTOL)
+    with pytest.raises(NotImplementedError):
+        lin.rmatvec(ints)
+
+
+def test_padded_qubits_and_single_qubit_and_zero_operator():
+    op = QubitOperator('X0 Y1', 0.5) + QubitOperator('Z1', -1.25)
+    for n in (2, 5, 11, 15):
+        v = _state(n, n)
+        assert helpers.close(LinearQubitOperator(op, n) * v, po.matvec(op.terms, n, v), RTOL)
+    one = QubitOperator('Y0', 2.0)
+    assert helpers.close(LinearQubitOperator(one) * numpy.array([1.0, 2.0]), [-4j, 2j], RTOL)
+    assert numpy.array_equal(LinearQubitOperator(QubitOperator(), 3) * numpy.ones(8), numpy.zeros(8))
+    ident = LinearQubitOperator(QubitOperator((), 3.0), 0)
+    assert numpy.array_equal(ident * numpy.array([2.0]), [6.0])
+
+
+def test_parallel_operator_matches_fused():
+    # linear_qubit_operator_test.py:191-284 semantics on one GPU
+    op = models.hubbard_jw(2, 3)
+    qop = QubitOperator()
+    qop.terms = dict(op.terms)
+    par = ParallelLinearQubitOperator(qop, 12, LinearQubitOperatorOptions(processes=3))
+    v = _state(12, 1)
+    want = po.matvec(qop.terms, 12, v)
+    assert helpers.close(par * v, want, RTOL)
+    parts = sum(lin * v for lin in par.linear_operators)
+    assert helpers.close(parts, want, RTOL)
+    assert par.options.pool is None
+    empty = ParallelLinearQubitOperator(QubitOperator(), 2)
+    assert numpy.array_equal(empty * numpy.ones(4), numpy.zeros(4))
+
+
+# ---- size-independent properties at sizes the oracle cannot reach ---------------------------
+@pytest.mark.parametrize('builder,n', [(lambda: models.hubbard_jw(3, 4), 24),
+                                       (lambda: models.molecular_jw(11, seed=1234), 22)])
+def test_hermiticity_and_linearity_properties(builder, n):
+    lin = LinearQubitOperator(builder(), n)
+    u, v = _state(n, 1), _state(n, 2)
+    hu, hv = lin * u, lin * v
+    # <u|Hv> = conj(<v|Hu>) for a Hermitian H
+    assert abs(numpy.vdot(u, hv) - numpy.conj(numpy.vdot(v, hu))) < 1e-11
+    comb = lin * (0.3 * u - 1.7j * v)
+    assert helpers.close(comb, 0.3 * hu - 1.7j * hv, 1e-12)
+    assert abs(expectation(lin, u) - numpy.vdot(u, hu)) < 1e-11
+    assert abs(expectation(lin, u).imag) < 1e-11
+
+
+# ---- CSC at larger sizes ----------------------------------------------------------------------
+def test_csc_dyadic_molecular_bit_exact():
+    """Dyadic coefficients: every column sum is exact, so structure and values are bit-exact
+    under any summation order (SURVEY.md section 8c finding 3)."""
+    op = models.molecular_jw(5, seed=1234, dyadic_bits=16)
+    got = qubit_operator_sparse(op, 10)
+    want = po.qubit_operator_sparse(op.terms, 10)
+    helpers.assert_csc_matches(got, want.indptr, want.indices, want.data, rtol=0)
+
+
+def test_csc_hubbard_n12_and_n16_bit_exact():
+    for dims in ((2, 3), (2, 4)):
+        op = models.hubbard_jw(*dims)
+        got = qubit_operator_sparse(op, op.n_qubits)
+        want = po.qubit_operator_sparse(op.terms, op.n_qubits)
+        helpers.assert_csc_matches(got, want.indptr, want.indices, want.data, rtol=0)
+
+
+def test_csc_generic_coefficients_residue_tolerant():
+    """Generic real coefficients: scipy's per-column std::sort (unstable above 16 entries)
+    decides which cancellation residues survive, so structure is compared after dropping
+    entries below 64*eps*sum|c_t| on both sides; all other entries must agree to 1e-12."""
+    op = models.molecular_jw(5, seed=1234)
+    got = qubit_operator_sparse(op, 10).tocoo()
+    want = po.qubit_operator_sparse(op.terms, 10).tocoo()
+    floor = 64 * numpy.finfo(float).eps * numpy.sum(numpy.abs(op.coeff))
+
+    def strong(m):
+        keep = numpy.abs(m.data) > floor
+        return scipy.sparse.csc_matrix((m.data[keep], (m.row[keep], m.col[keep])), shape=m.shape)
+
+    a, b = strong(got), strong(want)
+    assert numpy.array_equal(a.indptr, b.indptr) and numpy.array_equal(a.indices, b.indices)
+    assert numpy.max(numpy.abs(a.data - b.data)) <= 1e-12 * numpy.max(numpy.abs(b.data))
+    dense_diff = abs(got.tocsc() - want.tocsc())
+    assert dense_diff.max() <= floor
+
+
+def test_csc_matches_matrix_free_operator_columns():
+    op = models.random_pauli_sum(7, 60, 9, True)
+    mat = qubit_operator_sparse(op, 7).toarray()
+    cols = LinearQubitOperator(op, 7).matmat(numpy.eye(128, dtype=complex))
+    assert helpers.close(mat, cols, RTOL)
+
+
+def test_csc_fermion_route_equals_pauli_route_spectrum():
+    # sparse_tools_test.py:126-138
+    data = helpers.golden('fermion_cases.npz')
+    case = helpers.Case(data, 'molecular_6')
+    fop = helpers.fermion_operator_from(case['terms'], case['coeffs'])
+    f = jordan_wigner_sparse(fop, 6).toarray()
+    q = qubit_operator_sparse(models.molecular_jw(3, seed=5), 6).toarray()
+    assert numpy.allclose(numpy.linalg.eigvalsh(f), numpy.linalg.eigvalsh(q), atol=1e-10)

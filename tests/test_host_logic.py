@@ -1,0 +1,218 @@
+"""CPU: host-side logic (term compiler, stand-in operators, generators, API surface and
+error behaviour) and the C-ABI export check.  No compute calls: there is no GPU here."""
+import ctypes
+import os
+import re
+
+import numpy
+import pytest
+
+import helpers
+import pauli_oracle as po
+from openfermion_b200 import _lib, compiler, models
+from openfermion_b200.ops import FermionOperator, QubitOperator, count_qubits
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+# ---- C ABI ---------------------------------------------------------------------
+def _header_symbols():
+    text = open(os.path.join(ROOT, 'include', 'ofb200.h')).read()
+    text = re.sub(r'/\*.*?\*/', '', text, flags=re.S)
+    return sorted(set(re.findall(r'\b(ofb_[a-z0-9_]+)\s*\(', text)))
+
+
+def test_library_exports_every_header_symbol():
+    lib = ctypes.CDLL(_lib.LIB_PATH)
+    names = _header_symbols()
+    assert len(names) >= 50
+    for name in names:
+        assert hasattr(lib, name), name
+
+
+def test_ctypes_table_covers_header():
+    assert sorted(_lib.SIGNATURES) == _header_symbols()
+
+
+def test_library_loads_and_reports_version():
+    lib = _lib.load()
+    assert lib.ofb_version() == 100
+    assert lib.ofb_launch_count() >= 0
+
+
+def test_invalid_plan_arguments_are_rejected_without_gpu():
+    lib = _lib.load()
+    handle = ctypes.c_void_p()
+    x = numpy.array([1 << 5], dtype=numpy.uint64)
+    z = numpy.zeros(1, dtype=numpy.uint64)
+    c = numpy.ones(1, dtype=numpy.complex128)
+    status = lib.ofb_plan_create(3, 1, _lib.ptr(x), _lib.ptr(z), _lib.ptr(c), 0, ctypes.byref(handle))
+    assert status == 1  # OFB_ERR_INVALID: term acts outside n_qubits
+    assert b'outside n_qubits' in lib.ofb_last_error()
+
+
+@pytest.mark.skipif(_lib.device_count() > 0, reason='only meaningful without a GPU')
+def test_product_path_fails_loudly_without_gpu():
+    from openfermion_b200.linalg import LinearQubitOperator, qubit_operator_sparse
+    op = LinearQubitOperator(QubitOperator('X0'))  # construction needs no device
+    assert op.shape == (2, 2) and op.dtype == numpy.dtype(complex)
+    with pytest.raises(_lib.OfbError):
+        op * numpy.ones(2)
+    with pytest.raises(_lib.OfbError):
+        qubit_operator_sparse(QubitOperator('X0'))
+
+
+# ---- stand-in operators -----------------------------------------------------------
+def test_qubit_operator_parsing_and_products():
+    assert QubitOperator('X0 Y1').terms == {((0, 'X'), (1, 'Y')): 1.0}
+    assert QubitOperator(((1, 'Z'), (0, 'X')), 2.0).terms == {((0, 'X'), (1, 'Z')): 2.0}
+    assert (QubitOperator('X0') * QubitOperator('Y0')).terms == {((0, 'Z'),): 1j}
+    assert (QubitOperator('Y0') * QubitOperator('X0')).terms == {((0, 'Z'),): -1j}
+    assert (QubitOperator('Z0') * QubitOperator('X0')).terms == {((0, 'Y'),): 1j}
+    assert (QubitOperator('Y3') * QubitOperator('Y3')).terms == {(): 1.0}
+    total = QubitOperator('X0', 1.0) + QubitOperator('X0', -1.0)
+    assert total.terms == {}
+    assert count_qubits(QubitOperator('Z5')) == 6 and count_qubits(QubitOperator()) == 0
+
+
+def test_operator_groups_match_reference_slicing():
+    op = QubitOperator()
+    for q in range(7):
+        op += QubitOperator('Z%d' % q, q + 1.0)
+    groups = list(op.get_operator_groups(3))
+    assert [len(g.terms) for g in groups] == [len(t) for t in po.split_terms(op.terms, 3)]
+    merged = QubitOperator()
+    for g in groups:
+        merged += g
+    assert merged == op
+
+
+def test_fermion_operator_parsing():
+    assert FermionOperator('3^ 1').terms == {((3, 1), (1, 0)): 1.0}
+    assert count_qubits(FermionOperator('3^ 1')) == 4
+
+
+# ---- compiler -----------------------------------------------------------------------
+def test_mask_folding_follows_reference_bit_convention():
+    x, z, c = compiler.compile_qubit_terms(QubitOperator('X0 Y1 Z3', 2.0).terms, 4)
+    assert (int(x[0]), int(z[0])) == (0b1100, 0b0101)
+    for term in [(), ((0, 'Y'),), ((1, 'Z'), (2, 'X'))]:
+        xs, zs, _ = compiler.compile_qubit_terms({term: 1.0}, 3)
+        assert (int(xs[0]), int(zs[0])) == po.term_masks(term, 3)[:2]
+
+
+def test_compiler_rejects_symbolic_coefficients_and_small_n():
+    sympy = pytest.importorskip('sympy')
+    with pytest.raises(TypeError):
+        compiler.compile_qubit_terms({((0, 'X'),): sympy.Symbol('t')}, 1)
+    with pytest.raises(ValueError):
+        compiler.compile_qubit_terms({((3, 'X'),): 1.0}, 2)
+
+
+def _dense_from_rows(rows, n):
+    dim = 1 << n
+    mat = numpy.zeros((dim, dim), dtype=complex)
+    cols = numpy.arange(dim, dtype=numpy.uint64)
+    for om, ov, x, z, c in zip(*rows):
+        ok = (cols & om) == ov
+        sign = 1.0 - 2.0 * po.bit_parity(cols & z).astype(float)
+        mat[(cols ^ x)[ok].astype(int), cols[ok].astype(int)] += c * sign[ok]
+    return mat
+
+
+@pytest.mark.parametrize('case', helpers.fermion_cases(), ids=lambda c: c.name)
+def test_projected_rows_reproduce_reference_fermion_matrices(case):
+    op = helpers.fermion_operator_from(case['terms'], case['coeffs'])
+    rows = compiler.compile_fermion_terms(op.terms, case.n)
+    import scipy.sparse
+    want = scipy.sparse.csc_matrix((case['data'], case['indices'], case['indptr']),
+                                   shape=(2**case.n, 2**case.n)).toarray()
+    got = _dense_from_rows(rows, case.n)
+    assert numpy.max(numpy.abs(got - want)) <= 1e-12 * numpy.max(numpy.abs(want))
+    # structure: every stored reference entry is produced and nothing else is non-zero
+    assert numpy.array_equal(numpy.abs(got) > 1e-13, want != 0)
+
+
+def test_dead_fermion_terms_emit_nothing():
+    rows = compiler.compile_fermion_terms({((0, 1), (0, 1)): 1.0, ((1, 0), (1, 0)): 1.0,
+                                           ((0, 1), (0, 0)): 0.0}, 2)
+    assert len(rows[0]) == 0
+    rows = compiler.compile_fermion_terms({((0, 1), (0, 0)): 2.0}, 2)  # number operator
+    assert (int(rows[0][0]), int(rows[1][0]), int(rows[2][0])) == (0b10, 0b10, 0)
+
+
+# ---- generators -----------------------------------------------------------------------
+@pytest.mark.parametrize('name,builder', [
+    ('hubbard_2x2_jw', lambda: models.hubbard_jw(2, 2, 1.0, 4.0)),
+    ('hubbard_2x2_mu_h_jw', lambda: models.hubbard_jw(2, 2, 1.0, 4.0, 0.3, 0.2)),
+    ('hubbard_2x3_jw', lambda: models.hubbard_jw(2, 3, 1.0, 4.0)),
+    ('molecular_8_jw', lambda: models.molecular_jw(4, seed=1234)),
+])
+def test_generators_reproduce_reference_operators(name, builder):
+    data = helpers.golden('qubit_cases.npz')
+    ref = helpers.qubit_case_operator(helpers.Case(data, name))
+    ours = builder().terms
+    assert set(ours) == set(ref.terms)
+    assert max(abs(ours[k] - ref.terms[k]) for k in ours) < 1e-13
+
+
+def test_baseline_config_statistics():
+    # T and G of the BASELINE.json configs
+    for op, terms, groups in ((models.hubbard_jw(3, 4), 133, 49), (models.hubbard_jw(4, 4), 177, 65),
+                              (models.molecular_jw(10), 22351, 2536)):
+        assert (len(op), op.n_distinct_x()) == (terms, groups)
+
+
+def test_mask_operator_index_masks_match_compiler():
+    op = models.molecular_jw(3, seed=5)
+    x1, z1 = op.index_masks()
+    x2, z2, c2 = compiler.compile_qubit_terms(op.terms, op.n_qubits)
+    assert numpy.array_equal(x1, x2) and numpy.array_equal(z1, z2)
+    assert numpy.allclose(op.coeff, c2)
+
+
+def test_spin_orbital_tensors_layout():
+    rng = numpy.random.default_rng(0)
+    one, two = rng.normal(size=(2, 2)), rng.normal(size=(2, 2, 2, 2))
+    o, t = models.spin_orbital_tensors(one, two)
+    assert o[2, 0] == one[1, 0] and o[3, 1] == one[1, 0] and o[0, 1] == 0
+    assert t[0, 3, 1, 2] == two[0, 1, 0, 1] and t[1, 2, 0, 3] == two[0, 1, 0, 1]
+    assert t[2, 2, 0, 0] == two[1, 1, 0, 0] and t[0, 1, 0, 1] == 0
+
+
+# ---- API surface ------------------------------------------------------------------------
+def test_linalg_api_surface_and_errors():
+    from openfermion_b200 import linalg
+    for name in ['get_sparse_operator', 'qubit_operator_sparse', 'jordan_wigner_sparse',
+                 'LinearQubitOperator', 'ParallelLinearQubitOperator', 'LinearQubitOperatorOptions',
+                 'generate_linear_qubit_operator', 'get_linear_qubit_operator_diagonal', 'expectation',
+                 'variance', 'get_ground_state', 'get_gap', 'inner_product', 'Davidson',
+                 'DavidsonOptions', 'QubitDavidson', 'SparseDavidson', 'DavidsonError',
+                 'generate_random_vectors', 'append_random_vectors', 'orthonormalize']:
+        assert hasattr(linalg, name), name
+    with pytest.raises(ValueError):
+        linalg.LinearQubitOperator(QubitOperator('X3'), 1)
+    with pytest.raises(ValueError):
+        linalg.qubit_operator_sparse(QubitOperator('X3'), 1)
+    with pytest.raises(ValueError):
+        linalg.get_linear_qubit_operator_diagonal(QubitOperator('X3'), 1)
+    with pytest.raises(TypeError):
+        linalg.get_sparse_operator(1.0)
+    with pytest.raises(ValueError):
+        linalg.LinearQubitOperatorOptions(0)
+    with pytest.raises(ValueError):
+        linalg.DavidsonOptions(max_subspace=2)
+    with pytest.raises(ValueError):
+        linalg.DavidsonOptions(eps=0)
+    with pytest.raises(ValueError):
+        linalg.expectation(linalg.LinearQubitOperator(QubitOperator('X0')), [1, 0])
+    opts = linalg.DavidsonOptions()
+    assert (opts.max_subspace, opts.max_iterations, opts.eps, opts.real_only) == (100, 300, 1e-6, False)
+    opts.set_dimension(10)
+    assert opts.max_subspace == 11
+    par = linalg.ParallelLinearQubitOperator(QubitOperator('X0') + QubitOperator('Z1'), 2,
+                                             linalg.LinearQubitOperatorOptions(2))
+    assert par.options.pool is None and len(par.qubit_operator_groups) <= 2
+    assert len(par.linear_operators) == len(par.qubit_operator_groups)
+    assert isinstance(linalg.generate_linear_qubit_operator(QubitOperator('X0')), linalg.LinearQubitOperator)
+    assert linalg.inner_product(numpy.array([1j, 0]), numpy.array([1j, 0])) == 1

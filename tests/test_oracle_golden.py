@@ -1,0 +1,152 @@
+"""CPU: pins the oracle (oracle/pauli_oracle.py, oracle/pauli_oracle.c) against the
+reference's known-answer tests and against outputs of the real reference frozen in
+tests/golden/ by oracle/make_golden.py."""
+import numpy
+import pytest
+
+import c_oracle
+import pauli_oracle as po
+import helpers
+import known_answers as ka
+from openfermion_b200 import compiler, models
+from openfermion_b200.ops import QubitOperator, count_qubits
+
+
+@pytest.mark.parametrize('name,op,n,vec,expected', ka.MATVEC, ids=[k[0] for k in ka.MATVEC])
+def test_matvec_known_answers(name, op, n, vec, expected):
+    n = count_qubits(op) if n is None else n
+    assert numpy.allclose(po.matvec(op.terms, n, vec), expected)
+
+
+def test_matvec_compare_with_sparse():
+    # linear_qubit_operator_test.py:178-188
+    op = QubitOperator('X0 Y1 Z3')
+    mat = po.qubit_operator_sparse(op.terms).toarray()
+    cols = numpy.array([po.matvec(op.terms, 4, v) for v in numpy.identity(16)]).T
+    assert numpy.allclose(cols, mat)
+
+
+@pytest.mark.parametrize('name,op,n,data,indices,shape', ka.CSC, ids=[k[0] for k in ka.CSC])
+def test_csc_known_answers(name, op, n, data, indices, shape):
+    mat = po.qubit_operator_sparse(op.terms, n)
+    assert mat.shape == shape
+    assert list(mat.data) == data
+    assert list(mat.indices) == indices
+
+
+@pytest.mark.parametrize('name,op,n,expected', ka.DIAGONAL, ids=[k[0] for k in ka.DIAGONAL])
+def test_diagonal_known_answers(name, op, n, expected):
+    n = count_qubits(op) if n is None else n
+    assert numpy.allclose(po.diagonal(op.terms, n), expected)
+
+
+@pytest.mark.parametrize('string', ['Z1 X2 Y5', 'Z1 Z2 Z5'])
+def test_diagonal_equals_matvec_on_identity(string):
+    # sparse_tools_test.py:225-244
+    op = QubitOperator(string)
+    want = numpy.diag(po.matmat(op.terms, 6, numpy.eye(2**6)))
+    assert numpy.allclose(po.diagonal(op.terms, 6), want)
+
+
+def test_diagonal_complex_coefficient_raises_like_reference():
+    op = QubitOperator('Z0', 1.0 + 0.0j)
+    with pytest.raises(TypeError):
+        po.diagonal(op.terms, 1)
+
+
+def test_invalid_qubit_count():
+    with pytest.raises(ValueError):
+        po.qubit_operator_sparse(QubitOperator('X3').terms, 1)
+
+
+@pytest.mark.parametrize('case', helpers.qubit_cases(), ids=lambda c: c.name)
+def test_oracle_matches_reference_outputs(case):
+    op = helpers.qubit_case_operator(case)
+    n = case.n
+    assert numpy.array_equal(po.matvec(op.terms, n, case['vec']), case['matvec'])
+    mat = po.qubit_operator_sparse(op.terms, n)
+    helpers.assert_csc_matches(mat, case['indptr'], case['indices'], case['data'], rtol=0)
+    assert abs(po.expectation_terms(op.terms, n, case['vec']) - complex(case['expectation'])) \
+        <= 1e-13 * abs(complex(case['expectation'])) + 1e-300
+    if case.has('diagonal'):
+        assert numpy.array_equal(po.diagonal(op.terms, n), case['diagonal'])
+
+
+@pytest.mark.parametrize('case', helpers.fermion_cases(), ids=lambda c: c.name)
+def test_oracle_fermion_route_matches_reference(case):
+    op = helpers.fermion_operator_from(case['terms'], case['coeffs'])
+    mat = po.jordan_wigner_sparse(op.terms, case.n)
+    helpers.assert_csc_matches(mat, case['indptr'], case['indices'], case['data'], rtol=0)
+
+
+@pytest.mark.parametrize('case', helpers.qubit_cases(), ids=lambda c: c.name)
+def test_c_oracle_matches_numpy_oracle(case):
+    op = helpers.qubit_case_operator(case)
+    x, z, c = compiler.compile_qubit_terms(op.terms, case.n)
+    got = c_oracle.matvec(case.n, x, z, c, case['vec'])
+    assert helpers.close(got, case['matvec'], 1e-15)
+    if case.has('diagonal'):
+        assert helpers.close(c_oracle.diagonal(case.n, x, z, c), case['diagonal'], 1e-15)
+
+
+def test_ground_state_known_answer():
+    # sparse_tools_test.py:593-604
+    op = QubitOperator('Y0 X1') + QubitOperator('Z0 Z1')
+    energy, state = po.get_ground_state(po.qubit_operator_sparse(op.terms))
+    expected = numpy.array([0, 1j, 1, 0]) / numpy.sqrt(2.0)
+    assert abs(energy + 2) < 1e-7
+    assert abs(abs(numpy.vdot(expected, state)) - 1.0) < 1e-7
+
+
+def test_lih_ground_state_matches_file_energy():
+    # testing/lih_integration_test.py:70-71,103-106
+    data = helpers.golden('lih_sto3g.npz')
+    ham = models.molecular_hamiltonian(float(data['nuclear_repulsion']), data['one_body_integrals'],
+                                       data['two_body_integrals'])
+    from openfermion_b200.linalg.sparse_tools import _tensor_fermion_terms
+    fop = _tensor_fermion_terms(ham)
+    mat = po.jordan_wigner_sparse(fop.terms, 12)
+    assert mat.nnz == int(data['nnz'])
+    assert numpy.array_equal(mat.indptr, data['indptr'])
+    import hashlib
+    assert hashlib.sha256(mat.indices.tobytes()).hexdigest() == str(data['indices_sha256'])
+    energy, _ = po.get_ground_state(mat)
+    assert abs(energy - float(data['fci_energy'])) < 1e-7
+
+
+def test_oracle_davidson_reference_trajectory():
+    # davidson_test.py:205-215: exactly two iterations from e_0 give 1.41556103, not converged
+    dimension = 10
+    numpy.random.seed(dimension)
+    rand = numpy.array(numpy.random.rand(dimension, dimension))
+    numpy.random.seed(dimension * 2)
+    diag = numpy.array(range(dimension)) + numpy.random.rand(dimension)
+    matrix = rand + rand.conj().T + numpy.diag(diag)
+    guess = numpy.eye(dimension, 10)
+    ok, vals, _ = po.davidson_lowest_n(lambda v: matrix @ v, numpy.diag(matrix), 1, guess[:, :1],
+                                       max_iterations=2)
+    assert not ok and numpy.allclose(vals, [1.41556103])
+    ok, vals, _ = po.davidson_lowest_n(lambda v: matrix @ v, numpy.diag(matrix), 2, guess[:, :2],
+                                       max_iterations=5)
+    assert ok and numpy.allclose(vals, [1.15675714, 1.59132505])
+    ok, vals, _ = po.davidson_lowest_n(lambda v: matrix @ v, numpy.diag(matrix), 2, guess[:, :2],
+                                       max_iterations=5, max_subspace=8)
+    assert not ok and numpy.allclose(vals, [1.1572995, 1.61393264])
+
+
+@pytest.mark.needs_reference
+def test_oracle_against_live_reference():
+    """Build container only: fresh random operators through the real reference."""
+    import ref_shim
+    ref_shim.load()
+    from openfermion.linalg import LinearQubitOperator, qubit_operator_sparse
+    from openfermion.testing.testing_utils import random_qubit_operator
+    rng = numpy.random.default_rng(5)
+    for seed in range(100, 106):
+        n = 3 + seed % 6
+        op = random_qubit_operator(n, 20, n, seed=seed)
+        v = rng.normal(size=2**n) + 1j * rng.normal(size=2**n)
+        assert numpy.array_equal(LinearQubitOperator(op, n) * v, po.matvec(op.terms, n, v))
+        ref = qubit_operator_sparse(op, n)
+        helpers.assert_csc_matches(po.qubit_operator_sparse(op.terms, n), ref.indptr, ref.indices,
+                                   ref.data, rtol=0)
