@@ -97,8 +97,11 @@ class PauliPlan:
         _lib.call('ofb_csc_fill_host', self.handle, _lib.ptr(indptr), _lib.ptr(indices),
                   _lib.ptr(data), bits)
         if nnz.value == 0:
-            # the reference's empty result is float64
-            return scipy.sparse.csc_matrix((self.dim, self.dim), dtype=numpy.float64)
+            # With no terms at all the reference concatenates only its empty float seed lists
+            # and returns a float64 matrix; with terms that cancel it stays complex128
+            # (SURVEY.md section 7, quirk (c)).
+            dtype = numpy.float64 if self.n_terms == 0 else numpy.complex128
+            return scipy.sparse.csc_matrix((self.dim, self.dim), dtype=dtype)
         mat = scipy.sparse.csc_matrix((data, indices, indptr), shape=(self.dim, self.dim))
         mat.has_sorted_indices = True
         return mat

@@ -89,3 +89,28 @@ def close(got, want, rtol=1e-12):
     want = numpy.asarray(want)
     scale = max(float(numpy.max(numpy.abs(want))) if want.size else 0.0, 1e-300)
     return float(numpy.max(numpy.abs(got - want))) <= rtol * scale if want.size else True
+
+
+def assert_csc_matches_modulo_residues(got, indptr, indices, data, coeff_abs_sum, rtol=1e-12):
+    """Contract for Pauli-route columns holding more than 16 triplets with non-dyadic
+    coefficients (SURVEY.md section 8c): scipy's per-column std::sort is unstable there, so
+    which floating-point cancellation residues (|v| ~ 1e-16) survive eliminate_zeros depends
+    on its internal order.  Entries above 64*eps*sum|c_t| must match in position (bit-exact
+    indices) and value (rtol); everything else must be below that floor on both sides."""
+    import scipy.sparse
+    dim = got.shape[0]
+    want = scipy.sparse.csc_matrix((data, indices, indptr), shape=(dim, dim))
+    floor = 64 * numpy.finfo(float).eps * coeff_abs_sum
+
+    def strong(m):
+        m = m.tocoo()
+        keep = numpy.abs(m.data) > floor
+        out = scipy.sparse.csc_matrix((m.data[keep], (m.row[keep], m.col[keep])), shape=m.shape)
+        out.sort_indices()
+        return out
+
+    a, b = strong(got), strong(want)
+    assert numpy.array_equal(a.indptr, b.indptr) and numpy.array_equal(a.indices, b.indices)
+    assert numpy.max(numpy.abs(a.data - b.data)) <= rtol * numpy.max(numpy.abs(b.data))
+    assert abs(got - want).max() <= floor
+    assert got.has_sorted_indices and got.indices.dtype == indices.dtype
