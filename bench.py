@@ -293,6 +293,8 @@ def main():
     ap.add_argument('--qubits', type=int, default=28, help='N=1 workload size (even)')
     ap.add_argument('--e2e-steps', type=int, default=2)
     ap.add_argument('--no-cpu-baseline', action='store_true')
+    ap.add_argument('--dist-qubits', type=int, default=32, help='N>1 workload size (Hubbard)')
+    ap.add_argument('--dist-mode', default='nccl', choices=['nccl', 'p2p'])
     args = ap.parse_args()
     if args.impl == 'reference':
         return run_reference(args)

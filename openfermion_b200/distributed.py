@@ -1,0 +1,417 @@
+"""State vectors sharded by their high qubits across GPUs (one process per GPU).
+
+Rank r of W = 2^k owns amplitudes [r * 2^(n-k), (r+1) * 2^(n-k)): the top k index bits,
+i.e. OpenFermion qubits 0..k-1 (qubit q is index bit n-1-q,
+linalg/linear_qubit_operator.py:126).  For an x-group with mask x = (x_hi, x_lo):
+
+    out_r[j] += S_g((r << m) | j) * in_{r ^ x_hi}[j ^ x_lo]        m = n - k
+
+so a group is local when x_hi == 0 and otherwise needs the shard of the single peer
+r ^ x_hi -- a perfect matching of the ranks for every distinct non-zero x_hi ("pattern").
+Because the plan orders groups by ascending x, the groups of one pattern are a contiguous
+range.  Z bits on the high qubits only enter through the global index in S_g.
+
+Two data paths, same kernel (`ofb_apply_groups`):
+  * 'nccl'  pair exchange of whole shards with torch.distributed send/recv into staging
+            buffers, posted ahead and overlapped with the local groups;
+  * 'p2p'   no exchange at all: the kernel's input pointer is the peer's shard, mapped
+            through CUDA IPC, and the gather loads travel over NVLink while the SMs work
+            (compute and communication in one kernel).
+The reference has no counterpart (its only parallelism is term groups in worker processes
+over a replicated vector, linear_qubit_operator.py:176-209).
+
+The host logic (pattern table, peers, staging schedule, reductions) is independent of the
+device: tests drive it on CPU tensors over gloo with an injected local-apply function.
+"""
+import ctypes
+import json
+import os
+import time
+
+import numpy
+
+from openfermion_b200.compiler import compile_qubit_operator
+from openfermion_b200.ops import count_qubits
+
+
+# ----------------------------------------------------------------------------
+# host logic
+# ----------------------------------------------------------------------------
+class ShardLayout:
+    """Which x-group ranges need which peer shard."""
+
+    def __init__(self, n_qubits, world, x_mask):
+        if world < 1 or world & (world - 1):
+            raise ValueError('world size must be a power of two, got {}'.format(world))
+        self.n_qubits = n_qubits
+        self.world = world
+        self.shard_bits = world.bit_length() - 1
+        if self.shard_bits > n_qubits:
+            raise ValueError('more ranks than amplitudes')
+        self.local_bits = n_qubits - self.shard_bits
+        self.local_dim = 1 << self.local_bits
+        group_x = numpy.unique(numpy.asarray(x_mask, dtype=numpy.uint64))  # ascending = plan order
+        self.group_x = group_x
+        hi = (group_x >> numpy.uint64(self.local_bits)).astype(numpy.int64)
+        self.patterns = []  # (x_hi, g_begin, g_end), ascending x_hi, pattern 0 (local) first
+        start = 0
+        for g in range(1, len(hi) + 1):
+            if g == len(hi) or hi[g] != hi[start]:
+                self.patterns.append((int(hi[start]), start, g))
+                start = g
+        self.remote_patterns = [p for p in self.patterns if p[0] != 0]
+        self.local_pattern = next((p for p in self.patterns if p[0] == 0), None)
+
+    def peer(self, rank, x_hi):
+        return rank ^ x_hi
+
+    def index_base(self, rank):
+        return rank << self.local_bits
+
+    def exchange_bytes_per_matvec(self):
+        """Bytes each rank receives per matvec on the staged path."""
+        return len(self.remote_patterns) * self.local_dim * 16
+
+
+class TorchComm:
+    """All-reduce hook for the Krylov loops over a torch.distributed group."""
+
+    def __init__(self, dist, device, group=None):
+        self.dist = dist
+        self.group = group
+        self.device = device
+        self.rank = dist.get_rank(group)
+        self.world = dist.get_world_size(group)
+
+    def allsum(self, value):
+        import torch
+        value = complex(value)
+        t = torch.tensor([value.real, value.imag], dtype=torch.float64, device=self.device)
+        self.dist.all_reduce(t, group=self.group)
+        out = t.cpu()
+        return complex(float(out[0]), float(out[1]))
+
+    def barrier(self):
+        # an all-reduce orders the streams of all ranks without an extra host round trip
+        self.allsum(0.0)
+
+
+class ShardedPauliOperator:
+    """Matrix-free H|psi> on a sharded state.
+
+    local_apply(in_handle, out_handle, g_begin, g_end, accumulate) applies a group range to
+    this rank's output shard; the default launches the CUDA kernel.  `vectors` are opaque
+    handles created by `new_vector()` (device buffers; CPU arrays in the gloo tests).
+    """
+
+    def __init__(self, operator, n_qubits=None, dist=None, group=None, mode='nccl',
+                 max_staging=None, local_apply=None, vector_factory=None, tensor_of=None):
+        self.dist = dist
+        self.group = group
+        self.rank = dist.get_rank(group) if dist is not None else 0
+        self.world = dist.get_world_size(group) if dist is not None else 1
+        self.mode = mode
+        needed = count_qubits(operator)
+        self.n_qubits = needed if n_qubits is None else n_qubits
+        if self.n_qubits < needed:
+            raise ValueError('Invalid number of qubits specified.')
+        x, z, c = compile_qubit_operator(operator, self.n_qubits)
+        self.layout = ShardLayout(self.n_qubits, self.world, x)
+        self.n_terms = len(c)
+        self.n_groups = len(self.layout.group_x)
+        self.dim = self.layout.local_dim  # local length: what the Krylov loops see
+        self._cuda = local_apply is None
+        self._tables = (x, z, c)
+        self.plan = None
+        if self._cuda:
+            from openfermion_b200 import _lib
+            from openfermion_b200.plan import PauliPlan
+            self._lib = _lib
+            device = self._device_index()
+            _lib.call('ofb_set_device', ctypes.c_int(device))
+            self.plan = PauliPlan(self.n_qubits, x, z, c, device=device)
+            self._local_apply = self._cuda_apply
+            self._new = self._cuda_vector
+            self._tensor_of = self._cuda_tensor
+        else:
+            self._local_apply = local_apply
+            self._new = vector_factory
+            self._tensor_of = tensor_of
+        n_remote = len(self.layout.remote_patterns)
+        want = n_remote if max_staging is None else min(max_staging, n_remote)
+        self._staging = [self._new() for _ in range(want)] if mode == 'nccl' else []
+        self._peer_vectors = {}  # p2p: vector id -> list of per-rank device pointers
+        self._opened = []
+
+    # -- CUDA plumbing ---------------------------------------------------------------
+    def _device_index(self):
+        return int(os.environ.get('LOCAL_RANK', self.rank))
+
+    def _cuda_vector(self):
+        return self._lib.DeviceBuffer(self.dim * 16)
+
+    def _cuda_tensor(self, vec):
+        """float64 torch view of a raw device allocation (for NCCL send/recv)."""
+        import torch
+
+        class _Iface:
+            pass
+        holder = _Iface()
+        holder.__cuda_array_interface__ = {'shape': (2 * self.dim,), 'typestr': '<f8',
+                                           'data': (vec.ptr, False), 'version': 2}
+        return torch.as_tensor(holder, device='cuda:%d' % self._device_index())
+
+    def _stream(self):
+        import torch
+        return torch.cuda.current_stream().cuda_stream if self.dist is not None else None
+
+    def _cuda_apply(self, vin, vout, g_begin, g_end, accumulate):
+        src = vin if isinstance(vin, int) else vin.ptr
+        self.plan.apply_groups_device(src, vout.ptr, self.layout.local_bits,
+                                      self.layout.index_base(self.rank), g_begin, g_end,
+                                      1 if accumulate else 0, self._stream())
+
+    def new_vector(self):
+        return self._new()
+
+    # -- p2p registration ------------------------------------------------------------------
+    def register_peer_vectors(self, vectors):
+        """p2p mode: exchange CUDA IPC handles of the given local vectors once, so that later
+        matvecs can read any peer's copy of the same vector directly."""
+        import torch
+        lib = self._lib
+        handles = torch.zeros((len(vectors), 64), dtype=torch.uint8)
+        for i, vec in enumerate(vectors):
+            raw = (ctypes.c_ubyte * 64)()
+            lib.call('ofb_ipc_get_handle', ctypes.c_void_p(vec.ptr), raw)
+            handles[i] = torch.frombuffer(bytearray(raw), dtype=torch.uint8)
+        device = 'cuda:%d' % self._device_index()
+        gathered = [torch.zeros_like(handles, device=device) for _ in range(self.world)]
+        self.dist.all_gather(gathered, handles.to(device), group=self.group)
+        for i, vec in enumerate(vectors):
+            ptrs = []
+            for r in range(self.world):
+                if r == self.rank:
+                    ptrs.append(vec.ptr)
+                    continue
+                raw = (ctypes.c_ubyte * 64).from_buffer_copy(bytes(gathered[r][i].cpu().numpy()))
+                p = ctypes.c_void_p()
+                lib.call('ofb_ipc_open_handle', raw, ctypes.byref(p))
+                self._opened.append(p.value)
+                ptrs.append(p.value)
+            self._peer_vectors[vec.ptr] = ptrs
+
+    def close(self):
+        for p in self._opened:
+            try:
+                self._lib.call('ofb_ipc_close_handle', ctypes.c_void_p(p))
+            except Exception:
+                pass
+        self._opened = []
+
+    # -- the sharded matvec --------------------------------------------------------------------
+    def matvec(self, vin, vout):
+        """vout = (H vin) restricted to this rank's shard.  vin/vout: local shard handles."""
+        layout = self.layout
+        first = True
+        if self.mode == 'p2p' and layout.remote_patterns:
+            ptrs = self._peer_vectors.get(vin.ptr)
+            if ptrs is None:
+                raise RuntimeError('p2p mode: vector was not registered with register_peer_vectors')
+            for x_hi, g0, g1 in layout.patterns:
+                src = vin if x_hi == 0 else ptrs[layout.peer(self.rank, x_hi)]
+                self._local_apply(src, vout, g0, g1, not first)
+                first = False
+            if first:
+                self._local_apply(vin, vout, 0, 0, False)
+            return vout
+        remote = layout.remote_patterns
+        depth = len(self._staging)
+        if remote and depth == 0:
+            raise RuntimeError('no staging buffers for the exchange path')
+        works = {}
+
+        def post(i):
+            x_hi = remote[i][0]
+            peer = layout.peer(self.rank, x_hi)
+            dist = self.dist
+            ops = [dist.P2POp(dist.isend, self._tensor_of(vin), peer, self.group),
+                   dist.P2POp(dist.irecv, self._tensor_of(self._staging[i % depth]), peer, self.group)]
+            works[i] = dist.batch_isend_irecv(ops)
+
+        for i in range(min(depth, len(remote))):
+            post(i)
+        if layout.local_pattern is not None:
+            _, g0, g1 = layout.local_pattern
+            self._local_apply(vin, vout, g0, g1, False)
+            first = False
+        for i, (x_hi, g0, g1) in enumerate(remote):
+            for work in works.pop(i):
+                work.wait()
+            self._local_apply(self._staging[i % depth], vout, g0, g1, not first)
+            first = False
+            if i + depth < len(remote):
+                post(i + depth)  # enqueued after the kernel that still reads this buffer
+        if first:
+            self._local_apply(vin, vout, 0, 0, False)
+        return vout
+
+    # adapter for krylov.lanczos_lowest: raw pointers in, pointers out
+    def as_krylov_operator(self):
+        op = self
+
+        class _Adapter:
+            dim = op.dim
+
+            def __init__(self):
+                self._wrap = {}
+
+            def _vec(self, ptr):
+                if ptr not in self._wrap:
+                    class _View:
+                        pass
+                    v = _View()
+                    v.ptr = ptr
+                    self._wrap[ptr] = v
+                return self._wrap[ptr]
+
+            def apply(self, d_in, d_out, stream=None):
+                if op.mode == 'p2p' and op.layout.remote_patterns:
+                    raise RuntimeError('the Krylov adapter uses the staged exchange path')
+                op.matvec(self._vec(d_in), self._vec(d_out))
+        return _Adapter()
+
+
+def lanczos_ground_state(operator, dist, group=None, tol=1e-10, krylov_dim=None, max_restarts=40,
+                         seed=1234, stats=None):
+    """Distributed device-resident Lanczos (same loop as linalg.krylov, reductions over ranks).
+    Returns (energy, local shard of the eigenvector as numpy, residual norm)."""
+    from openfermion_b200.linalg import krylov
+    comm = TorchComm(dist, 'cuda:%d' % operator._device_index(), group)
+    theta, vec, residual = krylov.lanczos_lowest(operator.as_krylov_operator(), None, (), tol,
+                                                 krylov_dim, max_restarts, seed, comm, stats)
+    return theta, vec, residual
+
+
+# ----------------------------------------------------------------------------
+# bench entry for N > 1 (called by bench.py under torchrun)
+# ----------------------------------------------------------------------------
+def bench_main(args, metric, unit, clock_sampler_cls, measured_peak):
+    import torch
+    import torch.distributed as dist
+    from openfermion_b200 import _lib, models
+    from openfermion_b200.linalg import krylov
+
+    rank = int(os.environ.get('RANK', '0'))
+    world = int(os.environ.get('WORLD_SIZE', '1'))
+    local_rank = int(os.environ.get('LOCAL_RANK', rank))
+    os.environ.setdefault('MASTER_ADDR', '127.0.0.1')
+    torch.cuda.set_device(local_rank)
+    dist.init_process_group('nccl', device_id=torch.device('cuda', local_rank))
+    _lib.call('ofb_set_device', ctypes.c_int(local_rank))
+    n = args.dist_qubits
+    if n == 32:
+        op_model, name = models.hubbard_jw(4, 4), 'Fermi-Hubbard 4x4 spinful JW (t=1, U=4, periodic), 32 qubits'
+    else:
+        sites = n // 2
+        dims = {12: (2, 3), 16: (2, 4), 20: (2, 5), 24: (3, 4), 28: (2, 7), 30: (3, 5)}[sites * 2]
+        op_model, name = models.hubbard_jw(*dims), 'Fermi-Hubbard %dx%d spinful JW, %d qubits' % (dims + (n,))
+    mode = args.dist_mode
+    op = ShardedPauliOperator(op_model, n, dist=dist, mode=mode)
+    layout = op.layout
+    dim_local = op.dim
+    vin, vout = op.new_vector(), op.new_vector()
+    krylov.fill_random(dim_local, 42 + rank, False, vin.ptr)
+    comm = TorchComm(dist, 'cuda:%d' % local_rank)
+    krylov.scal(dim_local, 1.0 / krylov.gnorm(dim_local, vin.ptr, comm), vin.ptr)
+    if mode == 'p2p':
+        op.register_peer_vectors([vin])
+    T, G = op.n_terms, op.n_groups
+    start, stop = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+
+    def step():
+        if mode == 'p2p':
+            comm.barrier()  # peers must have finished writing the vector we are about to read
+        op.matvec(vin, vout)
+
+    for _ in range(args.warmup):
+        step()
+    torch.cuda.synchronize()
+    dist.barrier()
+    sampler = clock_sampler_cls(local_rank)
+    if rank == 0:
+        sampler.start()
+    launches0 = _lib.launch_count()
+    torch.cuda.synchronize()
+    start.record()
+    for _ in range(args.steps):
+        step()
+    stop.record()
+    torch.cuda.synchronize()
+    dist.barrier()
+    ms_local = start.elapsed_time(stop)
+    t = torch.tensor([ms_local], dtype=torch.float64, device='cuda')
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms = float(t.item())
+    launches = _lib.launch_count() - launches0
+    clocks = sampler.stop() if rank == 0 else None
+
+    # consistency: <v|Hv> must be real for a Hermitian H and identical on every rank
+    e = krylov.gdot(dim_local, vin.ptr, vout.ptr, comm)
+
+    # e2e: host shards in pinned memory -> device, matvec, result shard back to the host
+    e2e_steps = max(1, min(args.steps, args.e2e_steps))
+    vp = ctypes.c_void_p
+    h_in, h_out = vp(), vp()
+    nbytes = dim_local * 16
+    _lib.call('ofb_host_alloc', ctypes.byref(h_in), ctypes.c_size_t(nbytes))
+    _lib.call('ofb_host_alloc', ctypes.byref(h_out), ctypes.c_size_t(nbytes))
+    stream = vp(torch.cuda.current_stream().cuda_stream)
+    _lib.call('ofb_memcpy_d2h', h_in, vp(vin.ptr), ctypes.c_size_t(nbytes), stream)
+    torch.cuda.synchronize()
+    dist.barrier()
+    t0 = time.perf_counter()
+    for _ in range(e2e_steps):
+        _lib.call('ofb_memcpy_h2d', vp(vin.ptr), h_in, ctypes.c_size_t(nbytes), stream)
+        step()
+        _lib.call('ofb_memcpy_d2h', h_out, vp(vout.ptr), ctypes.c_size_t(nbytes), stream)
+        torch.cuda.synchronize()
+    dist.barrier()
+    e2e_s = time.perf_counter() - t0
+    t = torch.tensor([e2e_s], dtype=torch.float64, device='cuda')
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    e2e_s = float(t.item())
+    _lib.call('ofb_host_free', h_in)
+    _lib.call('ofb_host_free', h_out)
+
+    if rank == 0:
+        dim = float(1 << n)
+        seconds = ms / 1e3
+        value = T * dim * args.steps / seconds
+        peak, peak_src = measured_peak()
+        alg_bytes_rank = 16.0 * dim_local * (G + 1)
+        achieved = alg_bytes_rank / (seconds / args.steps) / 1e9
+        line = {
+            'metric': metric, 'value': value, 'unit': unit, 'n_gpus': world, 'steps': args.steps,
+            'warmup': args.warmup, 'ms_per_step': ms / args.steps, 'higher_is_better': True,
+            'scaling': 'strong', 'vs_baseline': None, 'dtype': 'f64', 'data': 'synthetic',
+            'config': {'workload': name, 'n_qubits': n, 'terms': T, 'x_groups': G,
+                       'sharding': 'top %d qubits over %d ranks' % (layout.shard_bits, world),
+                       'exchange': mode, 'remote_patterns': len(layout.remote_patterns),
+                       'exchange_bytes_per_rank_per_step': layout.exchange_bytes_per_matvec() if mode == 'nccl' else None,
+                       'l2_policy': 'inputs exceed L2 (%.1f GB per shard)' % (dim_local * 16 / 1e9),
+                       'timing': 'CUDA events, max over ranks', 'expectation_check': [e.real, e.imag]},
+            'clocks': clocks,
+            'e2e': {'value': T * dim * e2e_steps / e2e_s, 'unit': unit,
+                    'h2d_bytes_per_step': nbytes * world, 'd2h_bytes_per_step': nbytes * world,
+                    'steps': e2e_steps, 'path': 'pinned host shards -> ofb_apply_groups -> host'},
+            'gpu_launches': int(launches),
+            'roofline': {'bound': 'hbm', 'achieved': achieved, 'peak': peak, 'unit': 'GB/s',
+                         'frac': achieved / peak, 'traffic': None, 'peak_source': peak_src,
+                         'kernel': 'k_apply (per rank)', 'algorithmic_bytes_per_launch': alg_bytes_rank,
+                         'nvlink_bytes_per_rank_per_step': layout.exchange_bytes_per_matvec()},
+            'cpu_baseline': None,
+        }
+        print(json.dumps(line))
+    op.close()
+    dist.destroy_process_group()

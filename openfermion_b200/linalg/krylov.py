@@ -181,12 +181,34 @@ def apply_any(operator, state):
 # ----------------------------------------------------------------------------
 # Lanczos
 # ----------------------------------------------------------------------------
-def _project_out(n, basis_ptrs, w):
+class LocalComm:
+    """Reduction hook of the Krylov loops: identity on one GPU; the sharded path
+    (openfermion_b200.distributed) substitutes an all-reduce over the ranks."""
+    rank = 0
+    world = 1
+
+    def allsum(self, value):
+        return value
+
+
+_LOCAL = LocalComm()
+
+
+def gdot(n, x, y, comm=_LOCAL):
+    """conj(x) . y over all shards."""
+    return comm.allsum(dotc(n, x, y))
+
+
+def gnorm(n, x, comm=_LOCAL):
+    return float(numpy.sqrt(comm.allsum(dotc(n, x, x)).real))
+
+
+def _project_out(n, basis_ptrs, w, comm=_LOCAL):
     for u in basis_ptrs:
-        axpy(n, -dotc(n, u, w), u, w)
+        axpy(n, -gdot(n, u, w, comm), u, w)
 
 
-def _lanczos_pass(dev_op, start, locked, krylov_dim, tol, bufs, ritz=None):
+def _lanczos_pass(dev_op, start, locked, krylov_dim, tol, bufs, ritz=None, comm=_LOCAL):
     """One Lanczos sweep from `start` (device pointer, unit norm).
 
     ritz is None  -> builds T, returns (alphas, betas, theta, s, residual_estimate)
@@ -210,10 +232,10 @@ def _lanczos_pass(dev_op, start, locked, krylov_dim, tol, bufs, ritz=None):
                 break
         dev_op.apply(v, w)
         if locked:
-            _project_out(n, locked, w)
-        alpha = dotc(n, v, w).real
+            _project_out(n, locked, w, comm)
+        alpha = gdot(n, v, w, comm).real
         lanczos_update(n, alpha, beta_prev, v, v_prev if have_prev else None, w)
-        beta = nrm2(n, w)
+        beta = gnorm(n, w, comm)
         alphas.append(alpha)
         if ritz is None:
             check = (it < 32) or (it % 4 == 3) or it == steps - 1
@@ -238,7 +260,7 @@ def _lanczos_pass(dev_op, start, locked, krylov_dim, tol, bufs, ritz=None):
 
 
 def lanczos_lowest(dev_op, initial_guess=None, locked=(), tol=1e-10, krylov_dim=None,
-                   max_restarts=40, seed=1234):
+                   max_restarts=40, seed=1234, comm=_LOCAL, stats=None):
     """Lowest eigenpair of a Hermitian device operator, orthogonal to `locked` vectors.
 
     Returns (eigenvalue, device buffer holding the unit eigenvector, residual norm).
@@ -246,7 +268,7 @@ def lanczos_lowest(dev_op, initial_guess=None, locked=(), tol=1e-10, krylov_dim=
     n = dev_op.dim
     if krylov_dim is None:
         krylov_dim = 400
-    krylov_dim = max(2, min(krylov_dim, n - len(locked)))
+    krylov_dim = max(2, min(krylov_dim, n * comm.world - len(locked)))
     owners = {k: _lib.DeviceBuffer(n * C128) for k in 'abcy'}
     bufs = {k: b.ptr for k, b in owners.items()}
     start = _lib.DeviceBuffer(n * C128)
@@ -256,28 +278,32 @@ def lanczos_lowest(dev_op, initial_guess=None, locked=(), tol=1e-10, krylov_dim=
             raise ValueError('initial guess has the wrong dimension')
         upload(guess, start.ptr)
     else:
-        fill_random(n, seed, False, start.ptr)
+        fill_random(n, seed + 104729 * comm.rank, False, start.ptr)
     hy = _lib.DeviceBuffer(n * C128)
     theta = 0.0
     residual = numpy.inf
     for restart in range(max_restarts):
         if locked:
-            _project_out(n, locked, start.ptr)
-        norm = nrm2(n, start.ptr)
+            _project_out(n, locked, start.ptr, comm)
+        norm = gnorm(n, start.ptr, comm)
         if norm == 0.0:
-            fill_random(n, seed + 7919 * (restart + 1), False, start.ptr)
+            fill_random(n, seed + 7919 * (restart + 1) + 104729 * comm.rank, False, start.ptr)
             continue
         scal(n, 1.0 / norm, start.ptr)
-        alphas, betas, theta, s, _ = _lanczos_pass(dev_op, start.ptr, locked, krylov_dim, tol, bufs)
-        _lanczos_pass(dev_op, start.ptr, locked, krylov_dim, tol, bufs, ritz=s)
+        alphas, betas, theta, s, _ = _lanczos_pass(dev_op, start.ptr, locked, krylov_dim, tol, bufs,
+                                                   comm=comm)
+        _lanczos_pass(dev_op, start.ptr, locked, krylov_dim, tol, bufs, ritz=s, comm=comm)
+        if stats is not None:
+            stats['matvecs'] = stats.get('matvecs', 0) + 2 * len(alphas) - 1 + 1
+            stats['restarts'] = restart + 1
         y = bufs['y']
         if locked:
-            _project_out(n, locked, y)
-        scal(n, 1.0 / nrm2(n, y), y)
+            _project_out(n, locked, y, comm)
+        scal(n, 1.0 / gnorm(n, y, comm), y)
         dev_op.apply(y, hy.ptr)
-        theta = dotc(n, y, hy.ptr).real
+        theta = gdot(n, y, hy.ptr, comm).real
         axpy(n, -theta, y, hy.ptr)
-        residual = nrm2(n, hy.ptr)
+        residual = gnorm(n, hy.ptr, comm)
         copy(n, y, start.ptr)
         if residual <= 10.0 * tol * max(1.0, abs(theta)):
             break
