@@ -2,158 +2,197 @@
 //
 // Gather form:
 //     out[j] = sum_g S_g(j) * in[j ^ x_g],   S_g(j) = sum_{t in g} c_t (-1)^popc(j & z_t)
-// Each thread owns R amplitudes j_r = tile + r*BLOCK + tid (stride BLOCK so that every
-// 128-bit load/store instruction of a warp covers 512 contiguous bytes; XOR with x only
-// permutes lanes inside aligned blocks, so loads stay sector-coalesced for any mask).
-// The parity popc(j & z) is evaluated once per (thread, term) for r = 0; the other r differ
-// only in index bits log2(BLOCK).. and flip the sign by z's bits there, which is folded
-// into the high word of the coefficient with one LOP3 per (term, amplitude).  The running
-// S_g is a real scalar for groups whose phased coefficients are all real (or all
-// imaginary), so the common Hermitian/real case costs one DADD per term-amplitude and
-// 2 DFMA per (group, amplitude).  Term tables are read with warp-uniform 128-bit loads.
+//
+// Main kernel (k_apply8): a CTA of 256 threads owns a tile of 2048 amplitudes; thread `tid`
+// owns the 8 amplitudes j_r = tile + r*256 + tid, r = 0..7 (stride 256, so every 128-bit
+// load/store instruction of a warp covers 512 contiguous bytes and XOR with x only permutes
+// lanes inside aligned blocks: loads stay sector-coalesced for any mask).  The 8 amplitudes of
+// a thread differ only in index bits 8..10, so the sign of term t on amplitude r is
+//     sigma_t(j_0) * (-1)^popc(r & w_t),      w_t = (z_t >> 8) & 7   (the term's "class").
+// The plan stores each x-group's terms sorted by class (segments of <= 255 terms with the 8
+// class counts packed in one word), so a thread only accumulates the class sums
+//     A_w = sum_{t: w_t = w} sigma_t(j_0) c_t          -- ONE popc + ONE DADD per term --
+// and then expands them to its 8 amplitudes with a 3-stage in-register Walsh-Hadamard
+// butterfly, S_r = sum_w (-1)^popc(r & w) A_w (24 DADD per segment instead of 8 sign flips
+// and 8 adds per term).  out_r += S_r * in[j_r ^ x] is 2 DFMA per amplitude for groups whose
+// phased coefficients are all real (or all imaginary); complex groups run the real and the
+// imaginary table as two passes over the same loaded amplitudes.  Groups are executed in
+// ascending x, so consecutive groups re-read the same input tile through L1/L2; term tables
+// are read with warp-uniform 128-bit loads.
 #include "ofb_internal.cuh"
 
 namespace ofb {
 
 constexpr int BLOCK = 256;
-constexpr int BLOCK_BITS = 8;
+constexpr int R8 = 8;
+constexpr int TILE8 = BLOCK * R8;
+constexpr int TILE8_BITS = 11;
+static_assert(BLOCK == (1 << CLASS_SHIFT), "class bits must sit right above the thread index");
 
-__device__ __forceinline__ double flip_sign_hi(uint32_t hi, uint32_t lo) {
-    return __hiloint2double((int)hi, (int)lo);
+__device__ __forceinline__ double signed_coeff(double c, uint32_t parity) {
+    return __hiloint2double(__double2hiint(c) ^ (int)(parity << 31), __double2loint(c));
 }
 
-template <int R, bool Z32>
-struct TileIdx {
-    uint64_t j0;  // local index of amplitude r = 0
-    uint64_t jz;  // global index (index_base | j0) for the sign parity
-};
+template <bool Z32>
+__device__ __forceinline__ uint32_t sign_parity(uint64_t z, uint32_t j_lo, uint32_t base_hi) {
+    // parity of popc((index_base | j) & z); for n <= 32 everything lives in the low word
+    if (Z32) return (uint32_t)__popc(j_lo & (uint32_t)z);
+    return (uint32_t)(__popc(j_lo & (uint32_t)z) + __popc(base_hi & (uint32_t)(z >> 32)));
+}
 
-// sign bit (at bit 31) of amplitude r relative to amplitude 0: parity(r & (z >> BLOCK_BITS))
-template <int R>
-__device__ __forceinline__ void r_flips(uint64_t z, uint32_t (&flip)[R]) {
-    uint32_t zb = (uint32_t)(z >> BLOCK_BITS);
-    flip[0] = 0;
+// class sums A_w for one segment; t runs over the segment's terms in class order.  The next
+// table entry is always in flight (the tables carry one padding entry), so the load latency
+// overlaps the popc/xor/add chain of the current term, also across class boundaries.
+template <bool Z32>
+__device__ __forceinline__ void class_sums(const TermZC *tab, uint32_t t, uint64_t cls,
+                                           uint32_t j_lo, uint32_t base_hi, double (&A)[R8]) {
+    TermZC nxt = tab[t];
 #pragma unroll
-    for (int r = 1; r < R; ++r) {
-        // highest set bit k of r: flip[r] = flip[r - 2^k] ^ bit k of zb
-        int k = 31 - __builtin_clz((unsigned)r);
-        flip[r] = flip[r - (1 << k)] ^ ((zb << (31 - k)) & 0x80000000u);
+    for (int w = 0; w < R8; ++w) {
+        const uint32_t cnt = (uint32_t)(cls >> (8 * w)) & 0xffu;
+        double a = 0.0;
+#pragma unroll 1
+        for (uint32_t k = 0; k < cnt; ++k) {
+            const TermZC cur = nxt;
+            nxt = tab[++t];
+            a += signed_coeff(cur.c, sign_parity<Z32>(cur.z, j_lo, base_hi));
+        }
+        A[w] = a;
     }
 }
 
-template <int R, bool Z32, bool EXPECT>
-__global__ void __launch_bounds__(BLOCK)
-k_apply(const double2 *__restrict__ vin, double2 *__restrict__ vout,
-        const GroupDesc *__restrict__ groups, uint32_t g0, uint32_t g1,
-        const TermZC *__restrict__ zc, const double *__restrict__ ci, uint64_t dim,
-        uint64_t xmask_local, uint64_t index_base, int accumulate, double2 *__restrict__ partials) {
-    const uint64_t tile = (uint64_t)blockIdx.x * (uint64_t)(BLOCK * R);
-    const uint64_t j0 = tile + threadIdx.x;
-    const uint64_t jz = index_base | j0;
-    const uint32_t jz32 = (uint32_t)jz;
-
-    double ar[R], ai[R];
-    bool valid[R];
+// in-place Walsh-Hadamard transform: A[r] <- sum_w (-1)^popc(r & w) A[w]
+__device__ __forceinline__ void wht8(double (&A)[R8]) {
 #pragma unroll
-    for (int r = 0; r < R; ++r) {
-        uint64_t j = j0 + (uint64_t)r * BLOCK;
-        valid[r] = j < dim;
+    for (int h = 1; h < R8; h <<= 1) {
+#pragma unroll
+        for (int i = 0; i < R8; ++i) {
+            if ((i & h) == 0) {
+                double a = A[i], b = A[i | h];
+                A[i] = a + b;
+                A[i | h] = a - b;
+            }
+        }
+    }
+}
+
+// Shared-memory stage of one chunk: segment descriptors and both coefficient tables.
+struct StageBuf {
+    Segment segs[CHUNK_MAX_SEGS];
+    TermZC re[CHUNK_MAX_TERMS + 8];  // +8: the prefetching reader runs one entry ahead
+    TermZC im[CHUNK_MAX_TERMS + 8];
+};
+
+__device__ __forceinline__ void cp_async16(void *smem, const void *gmem) {
+    uint32_t sa = (uint32_t)__cvta_generic_to_shared(smem);
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(sa), "l"(gmem) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() {
+    asm volatile("cp.async.wait_group %0;\n" ::"n"(N) : "memory");
+}
+
+__device__ __forceinline__ void stage_chunk(StageBuf &b, const Chunk ck,
+                                            const Segment *__restrict__ segs,
+                                            const TermZC *__restrict__ zc_re,
+                                            const TermZC *__restrict__ zc_im, int has_imag) {
+    const char *gs = (const char *)(segs + ck.seg_begin);
+    char *ss = (char *)b.segs;
+    for (uint32_t u = threadIdx.x; u < ck.seg_count * 2; u += BLOCK) cp_async16(ss + u * 16, gs + u * 16);
+    for (uint32_t u = threadIdx.x; u < ck.term_count; u += BLOCK) {
+        cp_async16(&b.re[u], zc_re + ck.term_begin + u);
+        if (has_imag) cp_async16(&b.im[u], zc_im + ck.term_begin + u);
+    }
+    cp_async_commit();
+}
+
+template <bool Z32, bool EXPECT>
+__global__ void __launch_bounds__(BLOCK, 2)
+k_apply8(const double2 *__restrict__ vin, double2 *__restrict__ vout,
+         const Chunk *__restrict__ chunks, uint32_t c0, uint32_t c1,
+         const Segment *__restrict__ segs, uint32_t s0, uint32_t s1,
+         const TermZC *__restrict__ zc_re, const TermZC *__restrict__ zc_im, int has_imag,
+         uint32_t xmask_local, uint64_t index_base, int accumulate, double2 *__restrict__ partials) {
+    __shared__ StageBuf sbuf[2];
+    const uint32_t j0 = blockIdx.x * (uint32_t)TILE8 + threadIdx.x;  // local index of r = 0
+    const uint32_t j_lo = (uint32_t)index_base | j0;
+    const uint32_t base_hi = (uint32_t)(index_base >> 32);
+
+    double ar[R8], ai[R8];
+#pragma unroll
+    for (int r = 0; r < R8; ++r) {
         ar[r] = 0.0;
         ai[r] = 0.0;
-        if (!EXPECT && accumulate && valid[r]) {
-            double2 o = vout[j];
+    }
+    if (!EXPECT && accumulate) {
+#pragma unroll
+        for (int r = 0; r < R8; ++r) {
+            double2 o = vout[(size_t)(j0 + r * BLOCK)];
             ar[r] = o.x;
             ai[r] = o.y;
         }
     }
 
-    for (uint32_t g = g0; g < g1; ++g) {
-        const GroupDesc gd = groups[g];
-        const uint64_t xl = gd.x & xmask_local;
-        const uint32_t kind = gd.count >> 30;
-        const uint32_t tb = gd.begin, te = gd.begin + (gd.count & 0x3fffffffu);
-        double2 v[R];
-#pragma unroll
-        for (int r = 0; r < R; ++r) {
-            uint64_t j = (j0 + (uint64_t)r * BLOCK) ^ xl;
-            v[r] = valid[r] ? vin[j] : make_double2(0.0, 0.0);
-        }
-        if (kind != KIND_COMPLEX) {
-            double s[R];
-#pragma unroll
-            for (int r = 0; r < R; ++r) s[r] = 0.0;
-#pragma unroll 2
-            for (uint32_t t = tb; t < te; ++t) {
-                const TermZC e = zc[t];
-                uint32_t par = Z32 ? (uint32_t)__popc(jz32 & (uint32_t)e.z)
-                                   : (uint32_t)__popcll(jz & e.z);
-                uint32_t hi = (uint32_t)__double2hiint(e.c) ^ (par << 31);
-                uint32_t lo = (uint32_t)__double2loint(e.c);
-                uint32_t flip[R];
-                r_flips<R>(e.z, flip);
-#pragma unroll
-                for (int r = 0; r < R; ++r) s[r] += flip_sign_hi(hi ^ flip[r], lo);
-            }
-            if (kind == KIND_REAL) {
-#pragma unroll
-                for (int r = 0; r < R; ++r) {
-                    ar[r] = fma(s[r], v[r].x, ar[r]);
-                    ai[r] = fma(s[r], v[r].y, ai[r]);
-                }
-            } else {  // (i s) * (vx + i vy) = -s vy + i s vx
-#pragma unroll
-                for (int r = 0; r < R; ++r) {
-                    ar[r] = fma(-s[r], v[r].y, ar[r]);
-                    ai[r] = fma(s[r], v[r].x, ai[r]);
-                }
-            }
+    Chunk cur = chunks[c0];
+    Chunk nxt = (c0 + 1 < c1) ? chunks[c0 + 1] : cur;
+    stage_chunk(sbuf[0], cur, segs, zc_re, zc_im, has_imag);
+    for (uint32_t c = c0; c < c1; ++c) {
+        Chunk after = nxt;
+        if (c + 1 < c1) {
+            stage_chunk(sbuf[(c + 1 - c0) & 1], nxt, segs, zc_re, zc_im, has_imag);
+            if (c + 2 < c1) after = chunks[c + 2];
+            cp_async_wait<1>();
         } else {
-            double sr[R], si[R];
+            cp_async_wait<0>();
+        }
+        __syncthreads();
+        const StageBuf &b = sbuf[(c - c0) & 1];
+        const uint32_t lo = max(cur.seg_begin, s0), hi = min(cur.seg_begin + cur.seg_count, s1);
+        for (uint32_t s = lo; s < hi; ++s) {
+            const Segment sd = b.segs[s - cur.seg_begin];
+            const uint32_t jx = j0 ^ ((uint32_t)sd.x & xmask_local);
+            const uint32_t kind = sd.kind_count >> 30;
+            const uint32_t tl = sd.begin - cur.term_begin;
+            double2 v[R8];
 #pragma unroll
-            for (int r = 0; r < R; ++r) {
-                sr[r] = 0.0;
-                si[r] = 0.0;
-            }
-            for (uint32_t t = tb; t < te; ++t) {
-                const TermZC e = zc[t];
-                const double cim = ci[t];
-                uint32_t par = Z32 ? (uint32_t)__popc(jz32 & (uint32_t)e.z)
-                                   : (uint32_t)__popcll(jz & e.z);
-                uint32_t sgn = par << 31;
-                uint32_t hr = (uint32_t)__double2hiint(e.c) ^ sgn, lr = (uint32_t)__double2loint(e.c);
-                uint32_t hi = (uint32_t)__double2hiint(cim) ^ sgn, li = (uint32_t)__double2loint(cim);
-                uint32_t flip[R];
-                r_flips<R>(e.z, flip);
+            for (int r = 0; r < R8; ++r) v[r] = vin[(size_t)(jx ^ (uint32_t)(r << CLASS_SHIFT))];
+            double A[R8];
+            if (kind != KIND_IMAG) {  // real part of the coefficients
+                class_sums<Z32>(b.re, tl, sd.cls, j_lo, base_hi, A);
+                wht8(A);
 #pragma unroll
-                for (int r = 0; r < R; ++r) {
-                    sr[r] += flip_sign_hi(hr ^ flip[r], lr);
-                    si[r] += flip_sign_hi(hi ^ flip[r], li);
+                for (int r = 0; r < R8; ++r) {
+                    ar[r] = fma(A[r], v[r].x, ar[r]);
+                    ai[r] = fma(A[r], v[r].y, ai[r]);
                 }
             }
+            if (kind != KIND_REAL) {  // imaginary part: (i s)(vx + i vy) = -s vy + i s vx
+                class_sums<Z32>(b.im, tl, sd.cls, j_lo, base_hi, A);
+                wht8(A);
 #pragma unroll
-            for (int r = 0; r < R; ++r) {
-                ar[r] = fma(sr[r], v[r].x, ar[r]);
-                ar[r] = fma(-si[r], v[r].y, ar[r]);
-                ai[r] = fma(sr[r], v[r].y, ai[r]);
-                ai[r] = fma(si[r], v[r].x, ai[r]);
+                for (int r = 0; r < R8; ++r) {
+                    ar[r] = fma(-A[r], v[r].y, ar[r]);
+                    ai[r] = fma(A[r], v[r].x, ai[r]);
+                }
             }
         }
+        __syncthreads();  // everyone is done with this buffer before it is refilled
+        cur = nxt;
+        nxt = after;
     }
 
     if (!EXPECT) {
 #pragma unroll
-        for (int r = 0; r < R; ++r)
-            if (valid[r]) vout[j0 + (uint64_t)r * BLOCK] = make_double2(ar[r], ai[r]);
+        for (int r = 0; r < R8; ++r) vout[(size_t)(j0 + r * BLOCK)] = make_double2(ar[r], ai[r]);
     } else {
         // conj(in[j]) * (H in)[j], block-reduced in a fixed order (deterministic)
         double er = 0.0, ei = 0.0;
 #pragma unroll
-        for (int r = 0; r < R; ++r) {
-            if (valid[r]) {
-                double2 w = vin[j0 + (uint64_t)r * BLOCK];
-                er += w.x * ar[r] + w.y * ai[r];
-                ei += w.x * ai[r] - w.y * ar[r];
-            }
+        for (int r = 0; r < R8; ++r) {
+            double2 w = vin[(size_t)(j0 + r * BLOCK)];
+            er += w.x * ar[r] + w.y * ai[r];
+            ei += w.x * ai[r] - w.y * ar[r];
         }
 #pragma unroll
         for (int off = 16; off > 0; off >>= 1) {
@@ -179,6 +218,69 @@ k_apply(const double2 *__restrict__ vin, double2 *__restrict__ vout,
     }
 }
 
+// Small states (fewer than 2048 local amplitudes): one amplitude per thread, plain sums.
+template <bool EXPECT>
+__global__ void __launch_bounds__(BLOCK)
+k_apply1(const double2 *__restrict__ vin, double2 *__restrict__ vout,
+         const Segment *__restrict__ segs, uint32_t s0, uint32_t s1,
+         const TermZC *__restrict__ zc_re, const TermZC *__restrict__ zc_im, uint32_t dim,
+         uint64_t index_base, int accumulate, double2 *__restrict__ partials) {
+    const uint32_t j = blockIdx.x * BLOCK + threadIdx.x;
+    const bool valid = j < dim;
+    const uint64_t jz = index_base | j;
+    double ar = 0.0, ai = 0.0;
+    if (!EXPECT && accumulate && valid) {
+        double2 o = vout[j];
+        ar = o.x;
+        ai = o.y;
+    }
+    for (uint32_t s = s0; s < s1; ++s) {
+        const Segment sd = segs[s];
+        const uint32_t kind = sd.kind_count >> 30;
+        const uint32_t tb = sd.begin, te = sd.begin + (sd.kind_count & 0x3fffffffu);
+        const double2 v = valid ? vin[j ^ ((uint32_t)sd.x & (dim - 1))] : make_double2(0.0, 0.0);
+        double sr = 0.0, si = 0.0;
+        for (uint32_t t = tb; t < te; ++t) {
+            const TermZC a = zc_re[t];
+            const uint32_t par = (uint32_t)__popcll(jz & a.z);
+            if (kind != KIND_IMAG) sr += signed_coeff(a.c, par);
+            if (kind != KIND_REAL) si += signed_coeff(zc_im[t].c, par);
+        }
+        ar += sr * v.x - si * v.y;
+        ai += sr * v.y + si * v.x;
+    }
+    if (!EXPECT) {
+        if (valid) vout[j] = make_double2(ar, ai);
+    } else {
+        double er = 0.0, ei = 0.0;
+        if (valid) {
+            double2 w = vin[j];
+            er = w.x * ar + w.y * ai;
+            ei = w.x * ai - w.y * ar;
+        }
+#pragma unroll
+        for (int off = 16; off > 0; off >>= 1) {
+            er += __shfl_xor_sync(0xffffffffu, er, off);
+            ei += __shfl_xor_sync(0xffffffffu, ei, off);
+        }
+        __shared__ double sm[2 * (BLOCK / 32)];
+        int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+        if (lane == 0) {
+            sm[2 * warp] = er;
+            sm[2 * warp + 1] = ei;
+        }
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            double tr = 0.0, ti = 0.0;
+            for (int w = 0; w < BLOCK / 32; ++w) {
+                tr += sm[2 * w];
+                ti += sm[2 * w + 1];
+            }
+            partials[blockIdx.x] = make_double2(tr, ti);
+        }
+    }
+}
+
 // K3: diag[j] = sum over the x == 0 group of Re(c_t) (-1)^popc(j & z_t)
 template <bool Z32>
 __global__ void __launch_bounds__(BLOCK)
@@ -191,7 +293,7 @@ k_diagonal(double *__restrict__ out, const TermZC *__restrict__ zc, uint32_t tb,
         const TermZC e = zc[t];
         uint32_t par = Z32 ? (uint32_t)__popc((uint32_t)j & (uint32_t)e.z)
                            : (uint32_t)__popcll(j & e.z);
-        s += flip_sign_hi((uint32_t)__double2hiint(e.c) ^ (par << 31), (uint32_t)__double2loint(e.c));
+        s += signed_coeff(e.c, par);
     }
     out[j] = s;
 }
@@ -201,43 +303,38 @@ __global__ void k_zero_c128(double2 *out, uint64_t dim) {
     if (j < dim) out[j] = make_double2(0.0, 0.0);
 }
 
-static int pick_r(int local_bits) {
-    static int forced = -1;
-    if (forced < 0) {
-        const char *e = getenv("OFB_APPLY_R");
-        forced = e ? atoi(e) : 0;
-    }
-    if (forced == 1 || forced == 2 || forced == 4 || forced == 8) {
-        return (local_bits >= BLOCK_BITS + 3) ? forced : 1;
-    }
-    return local_bits >= 14 ? 4 : 1;
+static inline uint64_t apply_blocks(int local_bits) {
+    const uint64_t dim = 1ull << local_bits;
+    return local_bits >= TILE8_BITS ? dim / TILE8 : (dim + BLOCK - 1) / BLOCK;
 }
 
 template <bool EXPECT>
 static int launch_apply_impl(ofb_plan *p, const void *d_in, void *d_out, int local_bits,
                              uint64_t index_base, int64_t g0, int64_t g1, int accumulate,
-                             double2 *partials, int64_t *n_blocks_out, cudaStream_t s) {
+                             double2 *partials, cudaStream_t s) {
+    if (local_bits > 32) return fail(OFB_ERR_INVALID, "more than 2^32 amplitudes per device");
     const uint64_t dim = 1ull << local_bits;
-    const uint64_t xmask_local = dim - 1;
-    const int R = pick_r(local_bits);
-    const uint64_t per_block = (uint64_t)BLOCK * R;
-    const uint64_t blocks = (dim + per_block - 1) / per_block;
-    if (blocks > 0x7fffffffull) return fail(OFB_ERR_INVALID, "state too large for one launch");
-    if (n_blocks_out) *n_blocks_out = (int64_t)blocks;
+    const uint64_t blocks = apply_blocks(local_bits);
+    const uint32_t s0 = p->h_seg_begin[g0], s1 = p->h_seg_begin[g1];
+    if (s1 <= s0) return fail(OFB_ERR_STATE, "empty segment range");
+    const uint32_t c0 = p->h_chunk_of_seg[s0], c1 = p->h_chunk_of_seg[s1 - 1] + 1;
     const double2 *in = (const double2 *)d_in;
     double2 *out = (double2 *)d_out;
-    const bool z32 = p->z_fits32;
-#define OFB_GO(RR, ZZ)                                                                      \
-    k_apply<RR, ZZ, EXPECT><<<(unsigned)blocks, BLOCK, 0, s>>>(                             \
-        in, out, p->d_groups, (uint32_t)g0, (uint32_t)g1, p->d_zc, p->d_ci, dim, xmask_local, \
-        index_base, accumulate, partials)
-    switch (R) {
-        case 1: if (z32) OFB_GO(1, true); else OFB_GO(1, false); break;
-        case 2: if (z32) OFB_GO(2, true); else OFB_GO(2, false); break;
-        case 4: if (z32) OFB_GO(4, true); else OFB_GO(4, false); break;
-        default: if (z32) OFB_GO(8, true); else OFB_GO(8, false); break;
+    if (local_bits >= TILE8_BITS) {
+        const uint32_t xmask = (uint32_t)(dim - 1);
+        if (p->z_fits32)
+            k_apply8<true, EXPECT><<<(unsigned)blocks, BLOCK, 0, s>>>(
+                in, out, p->d_chunks, c0, c1, p->d_segs, s0, s1, p->d_zc, p->d_zc_im,
+                p->has_imag ? 1 : 0, xmask, index_base, accumulate, partials);
+        else
+            k_apply8<false, EXPECT><<<(unsigned)blocks, BLOCK, 0, s>>>(
+                in, out, p->d_chunks, c0, c1, p->d_segs, s0, s1, p->d_zc, p->d_zc_im,
+                p->has_imag ? 1 : 0, xmask, index_base, accumulate, partials);
+    } else {
+        k_apply1<EXPECT><<<(unsigned)blocks, BLOCK, 0, s>>>(in, out, p->d_segs, s0, s1, p->d_zc,
+                                                            p->d_zc_im, (uint32_t)dim, index_base,
+                                                            accumulate, partials);
     }
-#undef OFB_GO
     OFB_LAUNCH_CHECK();
     return OFB_OK;
 }
@@ -253,24 +350,21 @@ int launch_apply(ofb_plan *p, const void *d_in, void *d_out, int local_bits, uin
         return OFB_OK;
     }
     return launch_apply_impl<false>(p, d_in, d_out, local_bits, index_base, g0, g1, accumulate,
-                                    nullptr, nullptr, s);
+                                    nullptr, s);
 }
 
 int launch_expectation(ofb_plan *p, const void *d_state, double *h_out, cudaStream_t s) {
     h_out[0] = h_out[1] = 0.0;
     if (p->n_groups == 0) return OFB_OK;
     const int n = p->n_qubits;
-    const uint64_t dim = 1ull << n;
-    const int R = pick_r(n);
-    const uint64_t blocks = (dim + (uint64_t)BLOCK * R - 1) / ((uint64_t)BLOCK * R);
+    const uint64_t blocks = apply_blocks(n);
     int rc = ensure_partials(p, blocks * sizeof(double2) + 16);
     if (rc) return rc;
-    int64_t nb = 0;
     rc = launch_apply_impl<true>(p, d_state, nullptr, n, 0, 0, p->n_groups, 0,
-                                 (double2 *)p->d_partials, &nb, s);
+                                 (double2 *)p->d_partials, s);
     if (rc) return rc;
     double *d_res = p->d_partials + 2 * blocks;
-    rc = reduce_partials(p->d_partials, nb, 2, d_res, s);
+    rc = reduce_partials(p->d_partials, (int64_t)blocks, 2, d_res, s);
     if (rc) return rc;
     OFB_CUDA(cudaMemcpyAsync(p->h_pinned_scalars, d_res, 2 * sizeof(double), cudaMemcpyDeviceToHost, s));
     OFB_CUDA(cudaStreamSynchronize(s));
@@ -307,6 +401,8 @@ int ofb_apply_groups(ofb_plan *p, const void *d_in, void *d_out, int local_bits,
     if (g_begin < 0 || g_end > p->n_groups || g_begin > g_end)
         return fail(OFB_ERR_INVALID, "bad group range");
     if (d_in == d_out) return fail(OFB_ERR_INVALID, "d_in and d_out must not alias");
+    if (local_bits < 64 && (index_base & ((1ull << local_bits) - 1)))
+        return fail(OFB_ERR_INVALID, "index_base overlaps the local index bits");
     OFB_CUDA(cudaSetDevice(p->device));
     return launch_apply(p, d_in, d_out, local_bits, index_base, g_begin, g_end, accumulate,
                         (cudaStream_t)stream);

@@ -33,14 +33,33 @@ extern std::atomic<int64_t> g_launches;
 // One x-group of the gather form  out[j] += S_g(j) * in[j ^ x],
 // S_g(j) = sum_t c_t (-1)^popc(j & z_t)  (SURVEY.md section 0.4).
 enum GroupKind : uint32_t { KIND_COMPLEX = 0, KIND_REAL = 1, KIND_IMAG = 2 };
-struct __align__(16) GroupDesc {
+struct __align__(16) GroupDesc {  // scatter-form groups of the CSC builder
     uint64_t x;
-    uint32_t begin;  // first term
-    uint32_t count;  // bits 0..29 term count, bits 30..31 GroupKind
+    uint32_t begin;  // first row
+    uint32_t count;  // bits 0..29 row count
 };
-// Primary component of a term: real part (KIND_REAL / KIND_COMPLEX) or imaginary
-// part (KIND_IMAG) of c_t = coeff_t * (-i)^y_t, next to its z mask so that one
-// 128-bit uniform load fetches both.
+// Gather-form execution unit: at most 255 terms of one x-group, sorted by the "class"
+// w = (z >> CLASS_SHIFT) & 7, i.e. by the three z bits that distinguish the 8 amplitudes a
+// thread owns.  cls packs the 8 per-class term counts (byte w = count of class w).
+constexpr int CLASS_SHIFT = 8;  // log2(threads per block) of the apply kernel
+constexpr int SEG_MAX_TERMS = 255;
+struct __align__(16) Segment {
+    uint64_t x;
+    uint32_t begin;       // first term of the segment
+    uint32_t kind_count;  // bits 0..29 term count, bits 30..31 GroupKind
+    uint64_t cls;
+    uint64_t pad;
+};
+// Staging unit of the apply kernel: consecutive segments whose descriptors and term tables
+// are copied to shared memory together (double buffered with cp.async).
+constexpr int CHUNK_MAX_SEGS = 16;
+constexpr int CHUNK_MAX_TERMS = 256;
+struct __align__(16) Chunk {
+    uint32_t seg_begin, seg_count;
+    uint32_t term_begin, term_count;
+};
+// One component (real or imaginary part) of c_t = coeff_t * (-i)^y_t next to the z mask, so
+// that one 128-bit warp-uniform load fetches both.
 struct __align__(16) TermZC {
     uint64_t z;
     double c;
@@ -70,9 +89,15 @@ struct ofb_plan {
     std::vector<uint32_t> h_group_begin;  // n_groups + 1
     std::vector<uint32_t> h_group_kind;
     // device tables: gather form (apply / expectation / diagonal)
-    ofb::GroupDesc *d_groups = nullptr;
-    ofb::TermZC *d_zc = nullptr;
-    double *d_ci = nullptr;  // secondary component (imag part for KIND_COMPLEX)
+    std::vector<uint32_t> h_seg_begin;  // n_groups + 1: first segment of each logical group
+    std::vector<uint32_t> h_chunk_of_seg;  // chunk holding each segment
+    int64_t n_chunks = 0;
+    bool has_imag = false;  // some group has a non-real phased coefficient
+    ofb::Chunk *d_chunks = nullptr;
+    ofb::Segment *d_segs = nullptr;
+    ofb::TermZC *d_zc = nullptr;     // (z, Re c) in segment/class order
+    ofb::TermZC *d_zc_im = nullptr;  // (z, Im c) in the same order
+    ofb::GroupDesc *d_groups = nullptr;  // scatter-form groups (CSC)
     // device tables: scatter form (CSC)
     ofb::ScatterRow *d_rows = nullptr;
     uint32_t *d_sib = nullptr;  // [n_groups][n_qubits] sibling-subtree sizes

@@ -296,8 +296,6 @@ int ofb_plan_create(int n_qubits, int64_t n_terms, const uint64_t *x_mask, const
     std::iota(order.begin(), order.end(), 0u);
     std::stable_sort(order.begin(), order.end(), [&](uint32_t a, uint32_t b) { return x[a] < x[b]; });
 
-    std::vector<TermZC> zc(n_terms);
-    std::vector<double> ci(n_terms);
     std::vector<ScatterRow> rows(n_terms);
     std::vector<double> gr(n_terms), gi(n_terms);
     for (int64_t k = 0; k < n_terms; ++k) {
@@ -316,8 +314,14 @@ int ofb_plan_create(int n_qubits, int64_t n_terms, const uint64_t *x_mask, const
         ofb_plan_destroy(p);
         return rc;
     }
-    std::vector<GroupDesc> groups(p->n_groups);
+    // gather-form tables: per logical group, terms sorted by class and cut into segments
+    std::vector<Segment> segs;
+    std::vector<TermZC> zc_re, zc_im;
+    zc_re.reserve(n_terms + 1);
+    zc_im.reserve(n_terms + 1);
     p->h_group_kind.resize(p->n_groups);
+    p->h_seg_begin.assign(p->n_groups + 1, 0);
+    std::vector<uint32_t> idx;
     for (int64_t g = 0; g < p->n_groups; ++g) {
         uint32_t b = p->h_group_begin[g], e = p->h_group_begin[g + 1];
         bool all_real = true, all_imag = true;
@@ -327,16 +331,55 @@ int ofb_plan_create(int n_qubits, int64_t n_terms, const uint64_t *x_mask, const
         }
         uint32_t kind = all_real ? KIND_REAL : (all_imag ? KIND_IMAG : KIND_COMPLEX);
         p->h_group_kind[g] = kind;
-        for (uint32_t k = b; k < e; ++k) {
-            uint32_t t = order[k];
-            zc[k].z = z_mask[t];
-            zc[k].c = (kind == KIND_IMAG) ? gi[k] : gr[k];
-            ci[k] = (kind == KIND_COMPLEX) ? gi[k] : 0.0;
+        p->h_seg_begin[g] = (uint32_t)segs.size();
+        idx.resize(e - b);
+        std::iota(idx.begin(), idx.end(), b);
+        auto cls_of = [&](uint32_t k) { return (uint32_t)(z_mask[order[k]] >> CLASS_SHIFT) & 7u; };
+        std::stable_sort(idx.begin(), idx.end(),
+                         [&](uint32_t a, uint32_t c2) { return cls_of(a) < cls_of(c2); });
+        for (size_t pos = 0; pos < idx.size(); pos += SEG_MAX_TERMS) {
+            size_t end = std::min(idx.size(), pos + (size_t)SEG_MAX_TERMS);
+            // a chunk of a class-sorted list is still class-sorted
+            Segment sd{};
+            sd.x = p->h_group_x[g];
+            sd.begin = (uint32_t)zc_re.size();
+            sd.kind_count = (uint32_t)(end - pos) | (kind << 30);
+            uint64_t cls = 0;
+            for (size_t q = pos; q < end; ++q) {
+                uint32_t k = idx[q];
+                cls += 1ull << (8 * cls_of(k));
+                zc_re.push_back(TermZC{z_mask[order[k]], gr[k]});
+                zc_im.push_back(TermZC{z_mask[order[k]], gi[k]});
+            }
+            sd.cls = cls;
+            segs.push_back(sd);
         }
-        groups[g] = GroupDesc{p->h_group_x[g], b, (e - b) | (kind << 30)};
     }
-    if ((rc = upload(&p->d_groups, groups)) || (rc = upload(&p->d_zc, zc)) ||
-        (rc = upload(&p->d_ci, ci))) {
+    p->h_seg_begin[p->n_groups] = (uint32_t)segs.size();
+    // chunks: runs of <= CHUNK_MAX_SEGS segments holding <= CHUNK_MAX_TERMS terms
+    std::vector<Chunk> chunks;
+    p->h_chunk_of_seg.assign(segs.size(), 0);
+    for (size_t sidx = 0; sidx < segs.size(); ++sidx) {
+        uint32_t cnt = segs[sidx].kind_count & 0x3fffffffu;
+        if ((segs[sidx].kind_count >> 30) != KIND_REAL) p->has_imag = true;
+        if (chunks.empty() || chunks.back().seg_count >= (uint32_t)CHUNK_MAX_SEGS ||
+            chunks.back().term_count + cnt > (uint32_t)CHUNK_MAX_TERMS)
+            chunks.push_back(Chunk{(uint32_t)sidx, 0, segs[sidx].begin, 0});
+        chunks.back().seg_count += 1;
+        chunks.back().term_count += cnt;
+        p->h_chunk_of_seg[sidx] = (uint32_t)chunks.size() - 1;
+    }
+    p->n_chunks = (int64_t)chunks.size();
+    // one padding entry so that a software-prefetched load past the end stays in bounds
+    zc_re.push_back(TermZC{0, 0.0});
+    zc_im.push_back(TermZC{0, 0.0});
+    std::vector<GroupDesc> groups(p->n_groups);
+    for (int64_t g = 0; g < p->n_groups; ++g)
+        groups[g] = GroupDesc{p->h_group_x[g], p->h_group_begin[g],
+                              p->h_group_begin[g + 1] - p->h_group_begin[g]};
+    if ((rc = upload(&p->d_chunks, chunks)) || (rc = upload(&p->d_segs, segs)) ||
+        (rc = upload(&p->d_zc, zc_re)) ||
+        (rc = upload(&p->d_zc_im, zc_im)) || (rc = upload(&p->d_groups, groups))) {
         ofb_plan_destroy(p);
         return rc;
     }
@@ -387,8 +430,10 @@ int ofb_plan_destroy(ofb_plan *p) {
     if (!p) return OFB_OK;
     cudaSetDevice(p->device);
     cudaFree(p->d_groups);
+    cudaFree(p->d_segs);
+    cudaFree(p->d_chunks);
     cudaFree(p->d_zc);
-    cudaFree(p->d_ci);
+    cudaFree(p->d_zc_im);
     cudaFree(p->d_rows);
     cudaFree(p->d_sib);
     cudaFree(p->d_colptr);
