@@ -40,39 +40,82 @@ __device__ __forceinline__ uint32_t sign_parity(uint64_t z, uint32_t j_lo, uint3
     return (uint32_t)(__popc(j_lo & (uint32_t)z) + __popc(base_hi & (uint32_t)(z >> 32)));
 }
 
-// class sums A_w for one segment; t runs over the segment's terms in class order.  The next
-// table entry is always in flight (the tables carry one padding entry), so the load latency
-// overlaps the popc/xor/add chain of the current term, also across class boundaries.
+// sigma-signed sum of `cnt` consecutive table entries (one class run).  The sign is folded
+// into the high word with one add: hi + (parity << 31) flips bit 31 (mod 2^32).  Two entries
+// per iteration on independent accumulators; the loads of the next pair are issued before the
+// current pair is consumed, so the shared-memory latency overlaps the popc/add chains.
 template <bool Z32>
-__device__ __forceinline__ void class_sums(const TermZC *tab, uint32_t t, uint64_t cls,
-                                           uint32_t j_lo, uint32_t base_hi, double (&A)[R8]) {
-    TermZC nxt = tab[t];
+__device__ __forceinline__ double run_sum(const TermZC *tab, uint32_t cnt, uint32_t j_lo,
+                                          uint32_t base_hi) {
+    double a0 = 0.0, a1 = 0.0;
+    const TermZC *p = tab;
+    const TermZC *end2 = tab + (cnt & ~1u);
+    while (p != end2) {
+        const TermZC e0 = p[0], e1 = p[1];
+        p += 2;
+        a0 += __hiloint2double(__double2hiint(e0.c) + (int)(sign_parity<Z32>(e0.z, j_lo, base_hi) << 31),
+                               __double2loint(e0.c));
+        a1 += __hiloint2double(__double2hiint(e1.c) + (int)(sign_parity<Z32>(e1.z, j_lo, base_hi) << 31),
+                               __double2loint(e1.c));
+    }
+    if (cnt & 1u) {
+        const TermZC e0 = p[0];
+        a0 += __hiloint2double(__double2hiint(e0.c) + (int)(sign_parity<Z32>(e0.z, j_lo, base_hi) << 31),
+                               __double2loint(e0.c));
+    }
+    return a0 + a1;
+}
+
+// out_r += (+-a) * v_r (real pass) or (+- i a) * v_r (imaginary pass) with the static sign
+// (-1)^popc(r & W) of class W on amplitude r folded into the FMA operand modifiers.
+template <int W, bool IMAG>
+__device__ __forceinline__ void apply_class(double a, const double2 (&v)[R8], double (&ar)[R8],
+                                            double (&ai)[R8]) {
 #pragma unroll
-    for (int w = 0; w < R8; ++w) {
-        const uint32_t cnt = (uint32_t)(cls >> (8 * w)) & 0xffu;
-        double a = 0.0;
-#pragma unroll 1
-        for (uint32_t k = 0; k < cnt; ++k) {
-            const TermZC cur = nxt;
-            nxt = tab[++t];
-            a += signed_coeff(cur.c, sign_parity<Z32>(cur.z, j_lo, base_hi));
+    for (int r = 0; r < R8; ++r) {
+        const bool neg = (__builtin_popcount(r & W) & 1) != 0;
+        const double s = neg ? -a : a;
+        if (!IMAG) {
+            ar[r] = fma(s, v[r].x, ar[r]);
+            ai[r] = fma(s, v[r].y, ai[r]);
+        } else {  // (i s)(vx + i vy) = -s vy + i s vx
+            ar[r] = fma(-s, v[r].y, ar[r]);
+            ai[r] = fma(s, v[r].x, ai[r]);
         }
-        A[w] = a;
     }
 }
 
-// in-place Walsh-Hadamard transform: A[r] <- sum_w (-1)^popc(r & w) A[w]
-__device__ __forceinline__ void wht8(double (&A)[R8]) {
-#pragma unroll
-    for (int h = 1; h < R8; h <<= 1) {
-#pragma unroll
-        for (int i = 0; i < R8; ++i) {
-            if ((i & h) == 0) {
-                double a = A[i], b = A[i | h];
-                A[i] = a + b;
-                A[i | h] = a - b;
-            }
-        }
+template <bool IMAG>
+__device__ __forceinline__ void apply_class_dyn(uint32_t w, double a, const double2 (&v)[R8],
+                                                double (&ar)[R8], double (&ai)[R8]) {
+    switch (w) {
+        case 0: apply_class<0, IMAG>(a, v, ar, ai); break;
+        case 1: apply_class<1, IMAG>(a, v, ar, ai); break;
+        case 2: apply_class<2, IMAG>(a, v, ar, ai); break;
+        case 3: apply_class<3, IMAG>(a, v, ar, ai); break;
+        case 4: apply_class<4, IMAG>(a, v, ar, ai); break;
+        case 5: apply_class<5, IMAG>(a, v, ar, ai); break;
+        case 6: apply_class<6, IMAG>(a, v, ar, ai); break;
+        default: apply_class<7, IMAG>(a, v, ar, ai); break;
+    }
+}
+
+// all class runs of one segment from one coefficient table
+template <bool Z32, bool IMAG>
+__device__ __forceinline__ void segment_pass(const TermZC *tab, const Segment &sd, uint32_t j_lo,
+                                             uint32_t base_hi, const double2 (&v)[R8],
+                                             double (&ar)[R8], double (&ai)[R8]) {
+    const uint32_t runs = (sd.kind_count >> 24) & 0xfu;
+    uint64_t cnts = sd.cnts;
+    uint32_t ids = sd.ids;
+#pragma unroll 1
+    for (uint32_t k = 0; k < runs; ++k) {
+        const uint32_t cnt = (uint32_t)cnts & 0xffu;
+        const double a = run_sum<Z32>(tab, cnt, j_lo, base_hi);
+        apply_class_dyn<IMAG>(ids & 7u, a, v, ar, ai);
+        tab += cnt;
+        cnts >>= 8;
+        ids >>= 4;
     }
 }
 
@@ -157,25 +200,8 @@ k_apply8(const double2 *__restrict__ vin, double2 *__restrict__ vout,
             double2 v[R8];
 #pragma unroll
             for (int r = 0; r < R8; ++r) v[r] = vin[(size_t)(jx ^ (uint32_t)(r << CLASS_SHIFT))];
-            double A[R8];
-            if (kind != KIND_IMAG) {  // real part of the coefficients
-                class_sums<Z32>(b.re, tl, sd.cls, j_lo, base_hi, A);
-                wht8(A);
-#pragma unroll
-                for (int r = 0; r < R8; ++r) {
-                    ar[r] = fma(A[r], v[r].x, ar[r]);
-                    ai[r] = fma(A[r], v[r].y, ai[r]);
-                }
-            }
-            if (kind != KIND_REAL) {  // imaginary part: (i s)(vx + i vy) = -s vy + i s vx
-                class_sums<Z32>(b.im, tl, sd.cls, j_lo, base_hi, A);
-                wht8(A);
-#pragma unroll
-                for (int r = 0; r < R8; ++r) {
-                    ar[r] = fma(-A[r], v[r].y, ar[r]);
-                    ai[r] = fma(A[r], v[r].x, ai[r]);
-                }
-            }
+            if (kind != KIND_IMAG) segment_pass<Z32, false>(b.re + tl, sd, j_lo, base_hi, v, ar, ai);
+            if (kind != KIND_REAL) segment_pass<Z32, true>(b.im + tl, sd, j_lo, base_hi, v, ar, ai);
         }
         __syncthreads();  // everyone is done with this buffer before it is refilled
         cur = nxt;
@@ -237,7 +263,7 @@ k_apply1(const double2 *__restrict__ vin, double2 *__restrict__ vout,
     for (uint32_t s = s0; s < s1; ++s) {
         const Segment sd = segs[s];
         const uint32_t kind = sd.kind_count >> 30;
-        const uint32_t tb = sd.begin, te = sd.begin + (sd.kind_count & 0x3fffffffu);
+        const uint32_t tb = sd.begin, te = sd.begin + (sd.kind_count & 0xffffffu);
         const double2 v = valid ? vin[j ^ ((uint32_t)sd.x & (dim - 1))] : make_double2(0.0, 0.0);
         double sr = 0.0, si = 0.0;
         for (uint32_t t = tb; t < te; ++t) {

@@ -40,15 +40,17 @@ struct __align__(16) GroupDesc {  // scatter-form groups of the CSC builder
 };
 // Gather-form execution unit: at most 255 terms of one x-group, sorted by the "class"
 // w = (z >> CLASS_SHIFT) & 7, i.e. by the three z bits that distinguish the 8 amplitudes a
-// thread owns.  cls packs the 8 per-class term counts (byte w = count of class w).
+// thread owns.  Only the non-empty classes are listed: nibble k of `ids` is the class of the
+// k-th run of terms and byte k of `cnts` its length.
 constexpr int CLASS_SHIFT = 8;  // log2(threads per block) of the apply kernel
 constexpr int SEG_MAX_TERMS = 255;
 struct __align__(16) Segment {
     uint64_t x;
     uint32_t begin;       // first term of the segment
-    uint32_t kind_count;  // bits 0..29 term count, bits 30..31 GroupKind
-    uint64_t cls;
-    uint64_t pad;
+    uint32_t kind_count;  // bits 0..23 term count, bits 24..27 number of class runs, 30..31 kind
+    uint64_t cnts;
+    uint32_t ids;
+    uint32_t pad;
 };
 // Staging unit of the apply kernel: consecutive segments whose descriptors and term tables
 // are copied to shared memory together (double buffered with cp.async).

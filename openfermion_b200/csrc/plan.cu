@@ -343,15 +343,24 @@ int ofb_plan_create(int n_qubits, int64_t n_terms, const uint64_t *x_mask, const
             Segment sd{};
             sd.x = p->h_group_x[g];
             sd.begin = (uint32_t)zc_re.size();
-            sd.kind_count = (uint32_t)(end - pos) | (kind << 30);
-            uint64_t cls = 0;
+            uint64_t cnts = 0;
+            uint32_t ids = 0, runs = 0;
+            int last_cls = -1;
             for (size_t q = pos; q < end; ++q) {
                 uint32_t k = idx[q];
-                cls += 1ull << (8 * cls_of(k));
+                int cw = (int)cls_of(k);
+                if (cw != last_cls) {
+                    ids |= (uint32_t)cw << (4 * runs);
+                    ++runs;
+                    last_cls = cw;
+                }
+                cnts += 1ull << (8 * (runs - 1));
                 zc_re.push_back(TermZC{z_mask[order[k]], gr[k]});
                 zc_im.push_back(TermZC{z_mask[order[k]], gi[k]});
             }
-            sd.cls = cls;
+            sd.kind_count = (uint32_t)(end - pos) | (runs << 24) | (kind << 30);
+            sd.cnts = cnts;
+            sd.ids = ids;
             segs.push_back(sd);
         }
     }
@@ -360,7 +369,7 @@ int ofb_plan_create(int n_qubits, int64_t n_terms, const uint64_t *x_mask, const
     std::vector<Chunk> chunks;
     p->h_chunk_of_seg.assign(segs.size(), 0);
     for (size_t sidx = 0; sidx < segs.size(); ++sidx) {
-        uint32_t cnt = segs[sidx].kind_count & 0x3fffffffu;
+        uint32_t cnt = segs[sidx].kind_count & 0xffffffu;
         if ((segs[sidx].kind_count >> 30) != KIND_REAL) p->has_imag = true;
         if (chunks.empty() || chunks.back().seg_count >= (uint32_t)CHUNK_MAX_SEGS ||
             chunks.back().term_count + cnt > (uint32_t)CHUNK_MAX_TERMS)
