@@ -50,6 +50,7 @@ __device__ __forceinline__ double run_sum(const TermZC *tab, uint32_t cnt, uint3
     double a0 = 0.0, a1 = 0.0;
     const TermZC *p = tab;
     const TermZC *end2 = tab + (cnt & ~1u);
+#pragma unroll 1
     while (p != end2) {
         const TermZC e0 = p[0], e1 = p[1];
         p += 2;
@@ -117,6 +118,14 @@ __device__ __forceinline__ void segment_pass(const TermZC *tab, const Segment &s
         cnts >>= 8;
         ids >>= 4;
     }
+}
+
+// &base[index] with one IMAD.WIDE (the compiler otherwise shares the multiply and pays a
+// 64-bit add per amplitude)
+__device__ __forceinline__ const double2 *amp_ptr(const double2 *base, uint32_t index) {
+    const double2 *p;
+    asm("mad.wide.u32 %0, %1, 16, %2;" : "=l"(p) : "r"(index), "l"(base));
+    return p;
 }
 
 // Shared-memory stage of one chunk: segment descriptors and both coefficient tables.
@@ -199,7 +208,7 @@ k_apply8(const double2 *__restrict__ vin, double2 *__restrict__ vout,
             const uint32_t tl = sd.begin - cur.term_begin;
             double2 v[R8];
 #pragma unroll
-            for (int r = 0; r < R8; ++r) v[r] = vin[(size_t)(jx ^ (uint32_t)(r << CLASS_SHIFT))];
+            for (int r = 0; r < R8; ++r) v[r] = *amp_ptr(vin, jx ^ (uint32_t)(r << CLASS_SHIFT));
             if (kind != KIND_IMAG) segment_pass<Z32, false>(b.re + tl, sd, j_lo, base_hi, v, ar, ai);
             if (kind != KIND_REAL) segment_pass<Z32, true>(b.im + tl, sd, j_lo, base_hi, v, ar, ai);
         }
