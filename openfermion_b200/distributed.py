@@ -356,6 +356,36 @@ def bench_main(args, metric, unit, clock_sampler_cls, measured_peak):
     launches = _lib.launch_count() - launches0
     clocks = sampler.stop() if rank == 0 else None
 
+    diag = None
+    if getattr(args, 'dist_diagnose', False) and mode == 'nccl':
+        # where does the step time go: exchange alone, kernels alone (staging = stale data)
+        def timed(fn, reps=3):
+            torch.cuda.synchronize(); dist.barrier()
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record()
+            for _ in range(reps):
+                fn()
+            b.record(); torch.cuda.synchronize()
+            t = torch.tensor([a.elapsed_time(b) / reps], dtype=torch.float64, device='cuda')
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            return float(t.item())
+
+        def exchange_only():
+            for i, (x_hi, g0, g1) in enumerate(layout.remote_patterns):
+                peer = layout.peer(rank, x_hi)
+                ops = [dist.P2POp(dist.isend, op._tensor_of(vin), peer),
+                       dist.P2POp(dist.irecv, op._tensor_of(op._staging[i % len(op._staging)]), peer)]
+                for w in dist.batch_isend_irecv(ops):
+                    w.wait()
+
+        def kernels_only():
+            first = True
+            for x_hi, g0, g1 in layout.patterns:
+                src = vin if x_hi == 0 else op._staging[0]
+                op._local_apply(src, vout, g0, g1, not first)
+                first = False
+        diag = {'exchange_only_ms': timed(exchange_only), 'kernels_only_ms': timed(kernels_only)}
+
     # consistency: <v|Hv> must be real for a Hermitian H and identical on every rank
     e = krylov.gdot(dim_local, vin.ptr, vout.ptr, comm)
 
@@ -400,7 +430,8 @@ def bench_main(args, metric, unit, clock_sampler_cls, measured_peak):
                        'exchange': mode, 'remote_patterns': len(layout.remote_patterns),
                        'exchange_bytes_per_rank_per_step': layout.exchange_bytes_per_matvec() if mode == 'nccl' else None,
                        'l2_policy': 'inputs exceed L2 (%.1f GB per shard)' % (dim_local * 16 / 1e9),
-                       'timing': 'CUDA events, max over ranks', 'expectation_check': [e.real, e.imag]},
+                       'timing': 'CUDA events, max over ranks', 'expectation_check': [e.real, e.imag],
+                       'diagnose': diag},
             'clocks': clocks,
             'e2e': {'value': T * dim * e2e_steps / e2e_s, 'unit': unit,
                     'h2d_bytes_per_step': nbytes * world, 'd2h_bytes_per_step': nbytes * world,
