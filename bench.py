@@ -294,7 +294,7 @@ def main():
     ap.add_argument('--e2e-steps', type=int, default=2)
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--dist-qubits', type=int, default=32, help='N>1 workload size (Hubbard)')
-    ap.add_argument('--dist-mode', default='nccl', choices=['nccl', 'p2p'])
+    ap.add_argument('--dist-mode', default='ce', choices=['ce', 'nccl', 'p2p'])
     ap.add_argument('--dist-diagnose', action='store_true')
     args = ap.parse_args()
     if args.impl == 'reference':

@@ -11,7 +11,11 @@ r ^ x_hi -- a perfect matching of the ranks for every distinct non-zero x_hi ("p
 Because the plan orders groups by ascending x, the groups of one pattern are a contiguous
 range.  Z bits on the high qubits only enter through the global index in S_g.
 
-Two data paths, same kernel (`ofb_apply_groups`):
+Three data paths, same kernel (`ofb_apply_groups`):
+  * 'ce'    each rank PULLS the peer shards it needs into staging buffers with
+            device-to-device copies on a separate stream (copy engines over NVLink through
+            CUDA-IPC-mapped peer pointers: no SM is spent on communication) while the local
+            groups run; the kernels of a pattern wait on that copy's event;
   * 'nccl'  pair exchange of whole shards with torch.distributed send/recv into staging
             buffers, posted ahead and overlapped with the local groups;
   * 'p2p'   no exchange at all: the kernel's input pointer is the peer's shard, mapped
@@ -139,7 +143,9 @@ class ShardedPauliOperator:
             self._tensor_of = tensor_of
         n_remote = len(self.layout.remote_patterns)
         want = n_remote if max_staging is None else min(max_staging, n_remote)
-        self._staging = [self._new() for _ in range(want)] if mode == 'nccl' else []
+        self._staging = [self._new() for _ in range(want)] if mode in ('nccl', 'ce') else []
+        self._copy_stream = None
+        self._events = []
         self._peer_vectors = {}  # p2p: vector id -> list of per-rank device pointers
         self._opened = []
 
@@ -210,10 +216,68 @@ class ShardedPauliOperator:
         self._opened = []
 
     # -- the sharded matvec --------------------------------------------------------------------
+    def _matvec_ce(self, vin, vout):
+        """Copy-engine pull of the peer shards overlapped with the local groups."""
+        lib, layout = self._lib, self.layout
+        vp = ctypes.c_void_p
+        remote = layout.remote_patterns
+        ptrs = self._peer_vectors.get(vin.ptr)
+        if ptrs is None:
+            raise RuntimeError('ce mode: vector was not registered with register_peer_vectors')
+        if self._copy_stream is None:
+            s = vp()
+            lib.call('ofb_stream_create', ctypes.byref(s))
+            self._copy_stream = s
+            for _ in range(2 * max(len(self._staging), 1) + 1):
+                e = vp()
+                lib.call('ofb_event_create', ctypes.byref(e))
+                self._events.append(e)
+        depth = len(self._staging)
+        main = vp(self._stream())
+        copied = self._events[:depth]            # copy i landed in staging[i % depth]
+        consumed = self._events[depth:2 * depth]  # kernel finished reading staging[i % depth]
+        start = self._events[2 * depth]
+        nbytes = ctypes.c_size_t(self.dim * 16)
+        # copies may start once everything already queued on the main stream (the previous
+        # step's kernels, which read the staging buffers) is done
+        lib.call('ofb_event_record', start, main)
+        lib.call('ofb_stream_wait_event', self._copy_stream, start)
+
+        def post(i):
+            peer = layout.peer(self.rank, remote[i][0])
+            if i >= depth:
+                lib.call('ofb_stream_wait_event', self._copy_stream, consumed[i % depth])
+            lib.call('ofb_memcpy_d2d', vp(self._staging[i % depth].ptr), vp(ptrs[peer]), nbytes,
+                     self._copy_stream)
+            lib.call('ofb_event_record', copied[i % depth], self._copy_stream)
+
+        for i in range(min(depth, len(remote))):
+            post(i)
+        first = True
+        if layout.local_pattern is not None:
+            _, g0, g1 = layout.local_pattern
+            self._local_apply(vin, vout, g0, g1, False)
+            first = False
+        for i, (x_hi, g0, g1) in enumerate(remote):
+            lib.call('ofb_stream_wait_event', main, copied[i % depth])
+            self._local_apply(self._staging[i % depth], vout, g0, g1, not first)
+            first = False
+            lib.call('ofb_event_record', consumed[i % depth], main)
+            if i + depth < len(remote):
+                post(i + depth)
+        if first:
+            self._local_apply(vin, vout, 0, 0, False)
+        return vout
+
     def matvec(self, vin, vout):
-        """vout = (H vin) restricted to this rank's shard.  vin/vout: local shard handles."""
+        """vout = (H vin) restricted to this rank's shard.  vin/vout: local shard handles.
+        In the 'p2p' and 'ce' modes the caller must make sure (barrier) that every peer has
+        finished writing its copy of vin before this call and does not overwrite it before
+        all ranks have completed the call."""
         layout = self.layout
         first = True
+        if self.mode == 'ce' and layout.remote_patterns:
+            return self._matvec_ce(vin, vout)
         if self.mode == 'p2p' and layout.remote_patterns:
             ptrs = self._peer_vectors.get(vin.ptr)
             if ptrs is None:
@@ -282,6 +346,24 @@ class ShardedPauliOperator:
         return _Adapter()
 
 
+def init_nccl(local_rank):
+    """torch.distributed NCCL group whose communication streams have HIGH priority: the
+    exchange kernels must get SM slots while the (grid-filling) apply kernel is running,
+    otherwise the block scheduler drains the apply grid first and nothing overlaps."""
+    import torch
+    import torch.distributed as dist
+    torch.cuda.set_device(local_rank)
+    os.environ.setdefault('MASTER_ADDR', '127.0.0.1')
+    kwargs = {}
+    try:
+        opts = dist.ProcessGroupNCCL.Options(is_high_priority_stream=True)
+        kwargs['pg_options'] = opts
+    except Exception:
+        pass
+    dist.init_process_group('nccl', device_id=torch.device('cuda', local_rank), **kwargs)
+    return dist
+
+
 def lanczos_ground_state(operator, dist, group=None, tol=1e-10, krylov_dim=None, max_restarts=40,
                          seed=1234, stats=None):
     """Distributed device-resident Lanczos (same loop as linalg.krylov, reductions over ranks).
@@ -305,9 +387,7 @@ def bench_main(args, metric, unit, clock_sampler_cls, measured_peak):
     rank = int(os.environ.get('RANK', '0'))
     world = int(os.environ.get('WORLD_SIZE', '1'))
     local_rank = int(os.environ.get('LOCAL_RANK', rank))
-    os.environ.setdefault('MASTER_ADDR', '127.0.0.1')
-    torch.cuda.set_device(local_rank)
-    dist.init_process_group('nccl', device_id=torch.device('cuda', local_rank))
+    init_nccl(local_rank)
     _lib.call('ofb_set_device', ctypes.c_int(local_rank))
     n = args.dist_qubits
     if n == 32:
@@ -324,13 +404,13 @@ def bench_main(args, metric, unit, clock_sampler_cls, measured_peak):
     krylov.fill_random(dim_local, 42 + rank, False, vin.ptr)
     comm = TorchComm(dist, 'cuda:%d' % local_rank)
     krylov.scal(dim_local, 1.0 / krylov.gnorm(dim_local, vin.ptr, comm), vin.ptr)
-    if mode == 'p2p':
+    if mode in ('p2p', 'ce'):
         op.register_peer_vectors([vin])
     T, G = op.n_terms, op.n_groups
     start, stop = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
 
     def step():
-        if mode == 'p2p':
+        if mode in ('p2p', 'ce'):
             comm.barrier()  # peers must have finished writing the vector we are about to read
         op.matvec(vin, vout)
 
@@ -355,6 +435,9 @@ def bench_main(args, metric, unit, clock_sampler_cls, measured_peak):
     ms = float(t.item())
     launches = _lib.launch_count() - launches0
     clocks = sampler.stop() if rank == 0 else None
+
+    # consistency: <v|Hv> must be real for a Hermitian H and identical on every rank
+    e = krylov.gdot(dim_local, vin.ptr, vout.ptr, comm)
 
     diag = None
     if getattr(args, 'dist_diagnose', False) and mode == 'nccl':
@@ -385,9 +468,6 @@ def bench_main(args, metric, unit, clock_sampler_cls, measured_peak):
                 op._local_apply(src, vout, g0, g1, not first)
                 first = False
         diag = {'exchange_only_ms': timed(exchange_only), 'kernels_only_ms': timed(kernels_only)}
-
-    # consistency: <v|Hv> must be real for a Hermitian H and identical on every rank
-    e = krylov.gdot(dim_local, vin.ptr, vout.ptr, comm)
 
     # e2e: host shards in pinned memory -> device, matvec, result shard back to the host
     e2e_steps = max(1, min(args.steps, args.e2e_steps))
@@ -428,7 +508,7 @@ def bench_main(args, metric, unit, clock_sampler_cls, measured_peak):
             'config': {'workload': name, 'n_qubits': n, 'terms': T, 'x_groups': G,
                        'sharding': 'top %d qubits over %d ranks' % (layout.shard_bits, world),
                        'exchange': mode, 'remote_patterns': len(layout.remote_patterns),
-                       'exchange_bytes_per_rank_per_step': layout.exchange_bytes_per_matvec() if mode == 'nccl' else None,
+                       'exchange_bytes_per_rank_per_step': layout.exchange_bytes_per_matvec() if mode in ('nccl', 'ce') else None,
                        'l2_policy': 'inputs exceed L2 (%.1f GB per shard)' % (dim_local * 16 / 1e9),
                        'timing': 'CUDA events, max over ranks', 'expectation_check': [e.real, e.imag],
                        'diagnose': diag},

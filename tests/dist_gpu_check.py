@@ -21,8 +21,8 @@ from openfermion_b200.linalg import LinearQubitOperator, get_ground_state, krylo
 def main():
     rank, world = int(os.environ['RANK']), int(os.environ['WORLD_SIZE'])
     local = int(os.environ.get('LOCAL_RANK', rank))
-    torch.cuda.set_device(local)
-    dist.init_process_group('nccl', device_id=torch.device('cuda', local))
+    from openfermion_b200.distributed import init_nccl
+    init_nccl(local)
     _lib.call('ofb_set_device', ctypes.c_int(local))
     ok = True
     for name, op, n in (('hubbard_2x4', models.hubbard_jw(2, 4), 16),
@@ -30,12 +30,12 @@ def main():
                         ('dense_complex_14', models.random_pauli_sum(14, 300, 3, True), 14)):
         rng = numpy.random.default_rng(1)
         full = rng.normal(size=1 << n) + 1j * rng.normal(size=1 << n)
-        for mode in ('nccl', 'p2p'):
-            sop = ShardedPauliOperator(op, n, dist=dist, mode=mode, max_staging=1 if mode == 'nccl' else None)
+        for mode in ('nccl', 'p2p', 'ce'):
+            sop = ShardedPauliOperator(op, n, dist=dist, mode=mode, max_staging=1 if mode in ('nccl', 'ce') else None)
             ld = sop.dim
             vin, vout = sop.new_vector(), sop.new_vector()
             krylov.upload(full[rank * ld:(rank + 1) * ld], vin.ptr)
-            if mode == 'p2p':
+            if mode in ('p2p', 'ce'):
                 sop.register_peer_vectors([vin])
                 TorchComm(dist, 'cuda:%d' % local).barrier()
             sop.matvec(vin, vout)
