@@ -135,6 +135,17 @@ int ofb_diagonal_host(ofb_plan *plan, double *h_out);
  * buffers: indptr[2^n + 1], indices[nnz] (int32 or int64 per index_bits) and
  * data[nnz] complex128; rows ascending inside each column, exact zeros dropped. */
 int ofb_csc_count(ofb_plan *plan, int64_t *nnz, int *index_bits, void *stream);
+/* Summation order of duplicate entries (same row, same column) in the CSC passes:
+ *   mode 0  caller's term order (fast; identical to the reference whenever a column holds
+ *           <= 16 triplets or the sums are exact);
+ *   mode 1  the order scipy produces: coo->csc sorts every column's (row, value) pairs with
+ *           libstdc++ std::sort (unstable above 16 elements) before csr_sum_duplicates adds
+ *           equal rows left to right (linalg/sparse_tools.py:190-193 via scipy
+ *           sparsetools csr_sort_indices / csr_sum_duplicates).  The element movements of
+ *           std::sort are replayed per column, so even the floating-point cancellation
+ *           residues that survive eliminate_zeros match the reference bit for bit.
+ *           Cost O(T log T) per column.  Must be set before ofb_csc_count. */
+int ofb_plan_set_csc_mode(ofb_plan *plan, int mode);
 int ofb_csc_fill(ofb_plan *plan, void *d_indptr, void *d_indices, void *d_data, int index_bits,
                  void *stream);
 int ofb_csc_fill_host(ofb_plan *plan, void *h_indptr, void *h_indices, void *h_data,

@@ -66,6 +66,7 @@ SIGNATURES = {
     'ofb_diagonal': (c_int, [c_void_p, c_void_p, c_void_p]),
     'ofb_diagonal_host': (c_int, [c_void_p, c_void_p]),
     'ofb_csc_count': (c_int, [c_void_p, P(c_int64), P(c_int), c_void_p]),
+    'ofb_plan_set_csc_mode': (c_int, [c_void_p, c_int]),
     'ofb_csc_fill': (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_void_p]),
     'ofb_csc_fill_host': (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int]),
     'ofb_csr_matvec': (c_int, [c_int64, c_void_p, c_void_p, c_void_p, c_int, c_void_p, c_void_p,

@@ -178,7 +178,7 @@ int ofb_csc_count(ofb_plan *p, int64_t *nnz, int *index_bits, void *stream) {
     const int64_t nb = (int64_t)((dim + SB - 1) / SB);
     // colptr[dim + 1] then counts[dim] then block sums[nb]
     OFB_CUDA(cudaMalloc(&p->d_colptr, (2 * dim + 1 + nb + 1) * sizeof(int64_t)));
-    OFB_CUDA(cudaMalloc(&p->d_bitmap, (size_t)2 * std::max<uint32_t>(words, 1) * dim * sizeof(uint32_t)));
+    OFB_CUDA(cudaMalloc(&p->d_bitmap, p->csc_mode == 1 ? 16 : (size_t)2 * std::max<uint32_t>(words, 1) * dim * sizeof(uint32_t)));
     p->bitmap_words = words;
     int64_t *colptr = p->d_colptr, *counts = p->d_colptr + dim + 1, *bsums = counts + dim;
     uint32_t *bitmap = p->d_bitmap, *prefix = p->d_bitmap + (size_t)words * dim;
@@ -193,14 +193,19 @@ int ofb_csc_count(ofb_plan *p, int64_t *nnz, int *index_bits, void *stream) {
             OFB_CUDA(cudaMemcpy(p->d_groups, groups.data(), groups.size() * sizeof(GroupDesc),
                                 cudaMemcpyHostToDevice));
     }
-    const unsigned grid = (unsigned)((dim + CB - 1) / CB);
-    if (p->z_fits32)
-        k_csc_count<true><<<grid, CB, 0, s>>>(p->d_rows, p->d_groups, G, p->d_sib, p->n_qubits, dim,
-                                              words, bitmap, prefix, counts);
-    else
-        k_csc_count<false><<<grid, CB, 0, s>>>(p->d_rows, p->d_groups, G, p->d_sib, p->n_qubits, dim,
-                                               words, bitmap, prefix, counts);
-    OFB_LAUNCH_CHECK();
+    if (p->csc_mode == 1) {
+        int rc = csc_exact_count(p, counts, s);
+        if (rc) return rc;
+    } else {
+        const unsigned grid = (unsigned)((dim + CB - 1) / CB);
+        if (p->z_fits32)
+            k_csc_count<true><<<grid, CB, 0, s>>>(p->d_rows, p->d_groups, G, p->d_sib, p->n_qubits,
+                                                  dim, words, bitmap, prefix, counts);
+        else
+            k_csc_count<false><<<grid, CB, 0, s>>>(p->d_rows, p->d_groups, G, p->d_sib, p->n_qubits,
+                                                   dim, words, bitmap, prefix, counts);
+        OFB_LAUNCH_CHECK();
+    }
     k_scan_local<<<(unsigned)nb, SB, 0, s>>>(counts, (int64_t)dim, colptr, bsums);
     OFB_LAUNCH_CHECK();
     k_scan_sums<<<1, 32, 0, s>>>(bsums, nb, colptr + dim);
@@ -240,14 +245,20 @@ int ofb_csc_fill(ofb_plan *p, void *d_indptr, void *d_indices, void *d_data, int
     if (index_bits == 32) {
         k_convert_ptr<int32_t><<<pgrid, 256, 0, s>>>(p->d_colptr, (int64_t)dim + 1, (int32_t *)d_indptr);
         OFB_LAUNCH_CHECK();
-        if (p->csc_nnz > 0) {
+        if (p->csc_nnz > 0 && p->csc_mode == 1) {
+            int rc = csc_exact_fill(p, p->d_colptr, d_indices, d_data, 32, s);
+            if (rc) return rc;
+        } else if (p->csc_nnz > 0) {
             if (p->z_fits32) OFB_FILL(true, int32_t); else OFB_FILL(false, int32_t);
             OFB_LAUNCH_CHECK();
         }
     } else {
         k_convert_ptr<int64_t><<<pgrid, 256, 0, s>>>(p->d_colptr, (int64_t)dim + 1, (int64_t *)d_indptr);
         OFB_LAUNCH_CHECK();
-        if (p->csc_nnz > 0) {
+        if (p->csc_nnz > 0 && p->csc_mode == 1) {
+            int rc = csc_exact_fill(p, p->d_colptr, d_indices, d_data, 64, s);
+            if (rc) return rc;
+        } else if (p->csc_nnz > 0) {
             if (p->z_fits32) OFB_FILL(true, int64_t); else OFB_FILL(false, int64_t);
             OFB_LAUNCH_CHECK();
         }

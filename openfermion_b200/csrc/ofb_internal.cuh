@@ -72,7 +72,7 @@ struct __align__(16) ScatterRow {
     uint64_t z;
     uint64_t occ_mask;
     uint64_t occ_val;
-    uint64_t pad;
+    uint64_t x;
     double cr, ci;
 };
 
@@ -101,7 +101,11 @@ struct ofb_plan {
     ofb::TermZC *d_zc_im = nullptr;  // (z, Im c) in the same order
     ofb::GroupDesc *d_groups = nullptr;  // scatter-form groups (CSC)
     // device tables: scatter form (CSC)
-    ofb::ScatterRow *d_rows = nullptr;
+    ofb::ScatterRow *d_rows = nullptr;       // grouped by x (stable), for the fast CSC mode
+    ofb::ScatterRow *d_rows_orig = nullptr;  // caller's term order, for the scipy-order mode
+    int csc_mode = 0;                        // 0 = term-order sums, 1 = scipy sort-order emulation
+    uint64_t *d_sort_scratch = nullptr;      // exact mode: [n_terms][batch] (row << 32 | term)
+    int64_t sort_batch = 0;                  // columns per batch; == 2^n when one batch suffices
     uint32_t *d_sib = nullptr;  // [n_groups][n_qubits] sibling-subtree sizes
     // CSC state between count and fill
     int64_t *d_colptr = nullptr;   // 2^n + 1 exclusive scan of counts
@@ -126,6 +130,10 @@ int launch_apply(ofb_plan *plan, const void *d_in, void *d_out, int local_bits, 
                  int64_t g0, int64_t g1, int accumulate, cudaStream_t s);
 int launch_expectation(ofb_plan *plan, const void *d_state, double *h_out, cudaStream_t s);
 int launch_diagonal(ofb_plan *plan, double *d_out, cudaStream_t s);
+// csc_exact.cu: scipy-order (std::sort emulation) variants of the two CSC passes
+int csc_exact_count(ofb_plan *plan, int64_t *d_counts, cudaStream_t s);
+int csc_exact_fill(ofb_plan *plan, const int64_t *d_colptr, void *d_indices, void *d_data,
+                   int index_bits, cudaStream_t s);
 // shared reduction helper (vec.cu): sums `count` rows of `width` doubles
 int reduce_partials(const double *d_partials, int64_t count, int width, double *d_out,
                     cudaStream_t s);

@@ -111,6 +111,11 @@ static int finish_plan(ofb_plan *p, const std::vector<uint64_t> &x, const std::v
     build_sibling_table(p->h_group_x, p->n_qubits, sib);
     int rc;
     if ((rc = upload(&p->d_rows, rows_sorted))) return rc;
+    {
+        std::vector<ScatterRow> rows_orig(rows_sorted.size());
+        for (size_t k = 0; k < order.size(); ++k) rows_orig[order[k]] = rows_sorted[k];
+        if ((rc = upload(&p->d_rows_orig, rows_orig))) return rc;
+    }
     if ((rc = upload(&p->d_sib, sib))) return rc;
     OFB_CUDA(cudaMallocHost(&p->h_pinned_scalars, 64 * sizeof(double)));
     return OFB_OK;
@@ -307,7 +312,7 @@ int ofb_plan_create(int n_qubits, int64_t n_terms, const uint64_t *x_mask, const
         mul_neg_i_pow(sre, sim, (4 - (y & 3)) & 3);  // scatter form: coeff * (+i)^y
         gr[k] = re;
         gi[k] = im;
-        rows[k] = ScatterRow{z_mask[t], 0, 0, 0, sre, sim};
+        rows[k] = ScatterRow{z_mask[t], 0, 0, x_mask[t], sre, sim};
     }
     int rc = finish_plan(p, x, order, rows);
     if (rc) {
@@ -424,7 +429,7 @@ int ofb_plan_create_projected(int n_qubits, int64_t n_rows, const uint64_t *occ_
     std::vector<ScatterRow> rows(n_rows);
     for (int64_t k = 0; k < n_rows; ++k) {
         uint32_t t = order[k];
-        rows[k] = ScatterRow{z_mask[t], occ_mask[t], occ_val[t], 0, coeff_ri[2 * t], coeff_ri[2 * t + 1]};
+        rows[k] = ScatterRow{z_mask[t], occ_mask[t], occ_val[t], x_mask[t], coeff_ri[2 * t], coeff_ri[2 * t + 1]};
     }
     int rc = finish_plan(p, x, order, rows);
     if (rc) {
@@ -444,6 +449,8 @@ int ofb_plan_destroy(ofb_plan *p) {
     cudaFree(p->d_zc);
     cudaFree(p->d_zc_im);
     cudaFree(p->d_rows);
+    cudaFree(p->d_rows_orig);
+    cudaFree(p->d_sort_scratch);
     cudaFree(p->d_sib);
     cudaFree(p->d_colptr);
     cudaFree(p->d_bitmap);
@@ -453,6 +460,14 @@ int ofb_plan_destroy(ofb_plan *p) {
     if (p->h_pinned_scalars) cudaFreeHost(p->h_pinned_scalars);
     cudaGetLastError();
     delete p;
+    return OFB_OK;
+}
+
+int ofb_plan_set_csc_mode(ofb_plan *p, int mode) {
+    if (!p) return fail(OFB_ERR_INVALID, "plan is NULL");
+    if (mode != 0 && mode != 1) return fail(OFB_ERR_INVALID, "csc mode must be 0 or 1");
+    p->csc_mode = mode;
+    p->csc_nnz = -1;
     return OFB_OK;
 }
 

@@ -85,8 +85,30 @@ class PauliPlan:
         _lib.call('ofb_diagonal_host', self.handle, _lib.ptr(out))
         return out
 
-    def csc_host(self):
+    # term-order sums are bit-identical to the reference up to this many triplets per column
+    # (libstdc++'s std::sort is a stable insertion sort up to 16 elements)
+    STABLE_SORT_LIMIT = 16
+    # auto mode replays scipy's sort order while n_terms * 2^n stays below this
+    EXACT_MODE_BUDGET = 1 << 31
+
+    def csc_mode(self, mode=None):
+        """0 = term-order sums, 1 = scipy sort-order emulation (include/ofb200.h,
+        ofb_plan_set_csc_mode).  `mode` / $OFB_CSC_MODE: 'fast', 'exact' or 'auto' (default):
+        exact whenever it can differ from the fast mode and the replay is affordable."""
+        import os
+        mode = mode or os.environ.get('OFB_CSC_MODE', 'auto')
+        if mode == 'fast':
+            return 0
+        if mode == 'exact':
+            return 1
+        if mode != 'auto':
+            raise ValueError('csc mode must be fast, exact or auto')
+        needs = self.n_terms > self.STABLE_SORT_LIMIT
+        return 1 if needs and self.n_terms * self.dim <= self.EXACT_MODE_BUDGET else 0
+
+    def csc_host(self, mode=None):
         """Materialises the operator as scipy CSC with scipy's own index-width rule."""
+        _lib.call('ofb_plan_set_csc_mode', self.handle, c_int(self.csc_mode(mode)))
         nnz = c_int64()
         bits = c_int()
         _lib.call('ofb_csc_count', self.handle, ctypes.byref(nnz), ctypes.byref(bits), c_void_p(None))

@@ -24,7 +24,8 @@ RTOL = 1e-12
 # Golden Pauli-route cases with more than 16 triplets per column and generic real
 # coefficients: the reference's structure contains |v| ~ 1e-16 cancellation residues whose
 # survival depends on the internal order of scipy's unstable per-column std::sort
-# (SURVEY.md section 8c).  Every other golden case is compared bit-exactly.
+# (SURVEY.md section 8c).  The default ('auto') CSC mode replays that order and is compared
+# bit-exactly; the fast mode is compared modulo those residues.
 RESIDUE_CASES = {'molecular_6_jw', 'molecular_6_bk', 'molecular_8_jw'}
 
 
@@ -125,14 +126,44 @@ def test_golden_matvec_expectation_diagonal(case):
 
 @pytest.mark.parametrize('case', helpers.qubit_cases(), ids=lambda c: c.name)
 def test_golden_csc_pauli_route(case):
+    """Indices AND values bit-exact against the reference's own output for every golden case
+    (values compared with ==; the only tolerated difference is the sign of a zero part)."""
     op = helpers.qubit_case_operator(case)
     mat = qubit_operator_sparse(op, case.n)
-    if case.name not in RESIDUE_CASES:
-        helpers.assert_csc_matches(mat, case['indptr'], case['indices'], case['data'], RTOL)
-    else:
-        helpers.assert_csc_matches_modulo_residues(
-            mat, case['indptr'], case['indices'], case['data'],
-            float(numpy.sum(numpy.abs(case['coeffs']))), RTOL)
+    helpers.assert_csc_matches(mat, case['indptr'], case['indices'], case['data'], rtol=0)
+
+
+@pytest.mark.parametrize('name', sorted(RESIDUE_CASES))
+def test_golden_csc_pauli_route_fast_mode_contract(name, monkeypatch):
+    monkeypatch.setenv('OFB_CSC_MODE', 'fast')
+    case = helpers.Case(helpers.golden('qubit_cases.npz'), name)
+    mat = qubit_operator_sparse(helpers.qubit_case_operator(case), case.n)
+    helpers.assert_csc_matches_modulo_residues(
+        mat, case['indptr'], case['indices'], case['data'],
+        float(numpy.sum(numpy.abs(case['coeffs']))), RTOL)
+
+
+def test_csc_exact_mode_generic_molecular_n10_bit_exact():
+    """Generic (non-dyadic) coefficients, 1 519 terms per column: the scipy-order mode must
+    reproduce the oracle's (= scipy's) structure and values bit for bit."""
+    op = models.molecular_jw(5, seed=1234)
+    got = qubit_operator_sparse(op, 10)
+    want = po.qubit_operator_sparse(op.terms, 10)
+    helpers.assert_csc_matches(got, want.indptr, want.indices, want.data, rtol=0)
+
+
+def test_csc_exact_mode_multi_batch_and_fermion_route(monkeypatch):
+    monkeypatch.setenv('OFB_CSC_MODE', 'exact')
+    monkeypatch.setenv('OFB_SORT_BATCH', '256')  # several column batches, re-sorted in the fill pass
+    data = helpers.golden('fermion_cases.npz')
+    for name in ('molecular_8_dense', 'hubbard_2x3_open', 'molecular_4_complex'):
+        case = helpers.Case(data, name)
+        fop = helpers.fermion_operator_from(case['terms'], case['coeffs'])
+        mat = jordan_wigner_sparse(fop, case.n)
+        helpers.assert_csc_matches(mat, case['indptr'], case['indices'], case['data'], rtol=0)
+    case = helpers.Case(helpers.golden('qubit_cases.npz'), 'molecular_8_jw')
+    mat = qubit_operator_sparse(helpers.qubit_case_operator(case), case.n)
+    helpers.assert_csc_matches(mat, case['indptr'], case['indices'], case['data'], rtol=0)
 
 
 @pytest.mark.parametrize('case', helpers.fermion_cases(), ids=lambda c: c.name)
