@@ -9,7 +9,7 @@ import os
 import numpy
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, 'libofb200.so')
+LIB_PATH = os.environ.get('OFB_LIB_PATH') or os.path.join(_HERE, 'libofb200.so')
 
 c_void_p = ctypes.c_void_p
 c_int = ctypes.c_int

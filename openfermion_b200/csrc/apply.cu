@@ -3,12 +3,13 @@
 // Gather form:
 //     out[j] = sum_g S_g(j) * in[j ^ x_g],   S_g(j) = sum_{t in g} c_t (-1)^popc(j & z_t)
 //
-// Main kernel (k_apply8): a CTA of 256 threads owns a tile of 2048 amplitudes; thread `tid`
-// owns the 8 amplitudes j_r = tile + r*256 + tid, r = 0..7 (stride 256, so every 128-bit
+// Main kernel (k_apply8): a CTA of B = 128 threads owns a tile of 8B amplitudes; thread `tid`
+// owns the 8 amplitudes j_r = tile + r*B + tid, r = 0..7 (stride B, so every 128-bit
 // load/store instruction of a warp covers 512 contiguous bytes and XOR with x only permutes
 // lanes inside aligned blocks: loads stay sector-coalesced for any mask).  The 8 amplitudes of
-// a thread differ only in index bits 8..10, so the sign of term t on amplitude r is
-//     sigma_t(j_0) * (-1)^popc(r & w_t),      w_t = (z_t >> 8) & 7   (the term's "class").
+// a thread differ only in index bits s..s+2 (s = log2 B = CLASS_SHIFT), so the sign of term t
+// on amplitude r is
+//     sigma_t(j_0) * (-1)^popc(r & w_t),      w_t = (z_t >> s) & 7   (the term's "class").
 // The plan stores each x-group's terms sorted by class (segments of <= 255 terms with the 8
 // class counts packed in one word), so a thread only accumulates the class sums
 //     A_w = sum_{t: w_t = w} sigma_t(j_0) c_t          -- ONE popc + ONE DADD per term --
@@ -23,10 +24,10 @@
 
 namespace ofb {
 
-constexpr int BLOCK = 256;
+constexpr int BLOCK = 1 << OFB_APPLY_BLOCK_BITS;
 constexpr int R8 = 8;
 constexpr int TILE8 = BLOCK * R8;
-constexpr int TILE8_BITS = 11;
+constexpr int TILE8_BITS = OFB_APPLY_BLOCK_BITS + 3;
 static_assert(BLOCK == (1 << CLASS_SHIFT), "class bits must sit right above the thread index");
 
 __device__ __forceinline__ double signed_coeff(double c, uint32_t parity) {
@@ -160,7 +161,7 @@ __device__ __forceinline__ void stage_chunk(StageBuf &b, const Chunk ck,
 }
 
 template <bool Z32, bool EXPECT>
-__global__ void __launch_bounds__(BLOCK, 2)
+__global__ void __launch_bounds__(BLOCK, OFB_APPLY_MIN_CTAS)
 k_apply8(const double2 *__restrict__ vin, double2 *__restrict__ vout,
          const Chunk *__restrict__ chunks, uint32_t c0, uint32_t c1,
          const Segment *__restrict__ segs, uint32_t s0, uint32_t s1,

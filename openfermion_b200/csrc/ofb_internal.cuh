@@ -42,7 +42,13 @@ struct __align__(16) GroupDesc {  // scatter-form groups of the CSC builder
 // w = (z >> CLASS_SHIFT) & 7, i.e. by the three z bits that distinguish the 8 amplitudes a
 // thread owns.  Only the non-empty classes are listed: nibble k of `ids` is the class of the
 // k-th run of terms and byte k of `cnts` its length.
-constexpr int CLASS_SHIFT = 8;  // log2(threads per block) of the apply kernel
+#ifndef OFB_APPLY_BLOCK_BITS
+#define OFB_APPLY_BLOCK_BITS 7
+#endif
+#ifndef OFB_APPLY_MIN_CTAS
+#define OFB_APPLY_MIN_CTAS 4
+#endif
+constexpr int CLASS_SHIFT = OFB_APPLY_BLOCK_BITS;  // log2(threads per block) of the apply kernel
 constexpr int SEG_MAX_TERMS = 255;
 struct __align__(16) Segment {
     uint64_t x;

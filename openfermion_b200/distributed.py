@@ -321,8 +321,18 @@ class ShardedPauliOperator:
         return vout
 
     # adapter for krylov.lanczos_lowest: raw pointers in, pointers out
-    def as_krylov_operator(self):
+    def as_krylov_operator(self, comm=None):
+        """Operator view for the Krylov loops.  In the 'ce' / 'p2p' modes every new input
+        buffer is registered with the peers on first use (a collective: all ranks run the
+        same deterministic loop, so they meet here with corresponding buffers), and a
+        barrier before each application guarantees that the peers have finished writing
+        their shard of the input; the loop's next all-reduce orders the reads against any
+        later overwrite."""
         op = self
+
+        class _View:
+            def __init__(self, ptr):
+                self.ptr = ptr
 
         class _Adapter:
             dim = op.dim
@@ -332,17 +342,16 @@ class ShardedPauliOperator:
 
             def _vec(self, ptr):
                 if ptr not in self._wrap:
-                    class _View:
-                        pass
-                    v = _View()
-                    v.ptr = ptr
-                    self._wrap[ptr] = v
+                    self._wrap[ptr] = _View(ptr)
                 return self._wrap[ptr]
 
             def apply(self, d_in, d_out, stream=None):
-                if op.mode == 'p2p' and op.layout.remote_patterns:
-                    raise RuntimeError('the Krylov adapter uses the staged exchange path')
-                op.matvec(self._vec(d_in), self._vec(d_out))
+                vin = self._vec(d_in)
+                if op.mode in ('ce', 'p2p') and op.layout.remote_patterns:
+                    if d_in not in op._peer_vectors:
+                        op.register_peer_vectors([vin])
+                    comm.barrier()
+                op.matvec(vin, self._vec(d_out))
         return _Adapter()
 
 
@@ -370,7 +379,7 @@ def lanczos_ground_state(operator, dist, group=None, tol=1e-10, krylov_dim=None,
     Returns (energy, local shard of the eigenvector as numpy, residual norm)."""
     from openfermion_b200.linalg import krylov
     comm = TorchComm(dist, 'cuda:%d' % operator._device_index(), group)
-    theta, vec, residual = krylov.lanczos_lowest(operator.as_krylov_operator(), None, (), tol,
+    theta, vec, residual = krylov.lanczos_lowest(operator.as_krylov_operator(comm), None, (), tol,
                                                  krylov_dim, max_restarts, seed, comm, stats)
     return theta, vec, residual
 

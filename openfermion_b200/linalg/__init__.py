@@ -14,6 +14,11 @@ from openfermion_b200.linalg.sparse_tools import (
     get_sparse_operator,
     inner_product,
     jordan_wigner_sparse,
+    jw_get_ground_state_at_particle_number,
+    jw_number_indices,
+    jw_number_restrict_operator,
+    jw_sz_indices,
+    jw_sz_restrict_operator,
     qubit_operator_sparse,
     variance,
 )

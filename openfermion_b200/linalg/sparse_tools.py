@@ -172,3 +172,80 @@ def get_gap(sparse_operator, initial_guess=None):
 def inner_product(state_1, state_2):
     """conj(state_1) . state_2 (sparse_tools.py:1098-1100)."""
     return numpy.dot(state_1.conjugate(), state_2)
+
+
+# ----------------------------------------------------------------------------
+# SURVEY.md section 8f row N1: Jordan-Wigner symmetry-sector helpers
+# (sparse_tools.py:273-345, 375-423, 477-513).  Index selection is host arithmetic as in
+# the reference; the eigen-solve inside the sector runs on the device (CSR SpMV + Lanczos).
+# ----------------------------------------------------------------------------
+def jw_number_indices(n_electrons, n_qubits):
+    """Indices of all basis states with n_electrons occupied modes, in the reference's order
+    (itertools.combinations over bit positions, sparse_tools.py:273-292)."""
+    occupations = itertools.combinations(range(n_qubits), n_electrons)
+    return [sum(1 << n for n in occupation) for occupation in occupations]
+
+
+def jw_sz_indices(sz_value, n_qubits, n_electrons=None, up_index=None, down_index=None):
+    """Indices of basis states with fixed S_z (sparse_tools.py:295-372); up = 2i, down = 2i+1
+    by default (utils/indexing.py:17,29)."""
+    up_index = up_index or (lambda i: 2 * i)
+    down_index = down_index or (lambda i: 2 * i + 1)
+    if n_qubits % 2 != 0:
+        raise ValueError('Number of qubits must be even')
+    if not (2.0 * sz_value).is_integer():
+        raise ValueError('Sz value must be an integer or half-integer')
+    n_sites = n_qubits // 2
+    sz_integer = int(2.0 * sz_value)
+    indices = []
+
+    def pair(outer_map, n_outer, inner_map, n_inner):
+        # every arrangement of the outer spin species with every arrangement of the inner one
+        inner = list(itertools.combinations(range(n_sites), n_inner))
+        for outer_occ in itertools.combinations(range(n_sites), n_outer):
+            outer_modes = [outer_map(i) for i in outer_occ]
+            for inner_occ in inner:
+                occupation = outer_modes + [inner_map(i) for i in inner_occ]
+                indices.append(sum(1 << (n_qubits - 1 - m) for m in occupation))
+
+    if n_electrons is not None:
+        if (n_electrons + sz_integer) % 2 != 0 or n_electrons < abs(sz_integer):
+            raise ValueError('The specified particle number and sz value are incompatible.')
+        num_up = (n_electrons + sz_integer) // 2
+        pair(up_index, num_up, down_index, n_electrons - num_up)
+    else:
+        more_map, less_map = (down_index, up_index) if sz_integer < 0 else (up_index, down_index)
+        for n in range(abs(sz_integer), n_sites + 1):
+            pair(more_map, n, less_map, n - abs(sz_integer))
+    return indices
+
+
+def jw_number_restrict_operator(operator, n_electrons, n_qubits=None):
+    if n_qubits is None:
+        n_qubits = int(numpy.log2(operator.shape[0]))
+    select = jw_number_indices(n_electrons, n_qubits)
+    return operator[numpy.ix_(select, select)]
+
+
+def jw_sz_restrict_operator(operator, sz_value, n_electrons=None, n_qubits=None, up_index=None,
+                            down_index=None):
+    if n_qubits is None:
+        n_qubits = int(numpy.log2(operator.shape[0]))
+    select = jw_sz_indices(sz_value, n_qubits, n_electrons=n_electrons, up_index=up_index,
+                           down_index=down_index)
+    return operator[numpy.ix_(select, select)]
+
+
+def jw_get_ground_state_at_particle_number(sparse_operator, particle_number):
+    """Lowest eigenpair inside a particle-number sector, expanded back to 2^n amplitudes
+    (sparse_tools.py:477-513)."""
+    n_qubits = int(numpy.log2(sparse_operator.shape[0]))
+    restricted = jw_number_restrict_operator(sparse_operator, particle_number, n_qubits)
+    if restricted.shape[0] - 1 <= 1:
+        eigvals, eigvecs = numpy.linalg.eigh(restricted.toarray())
+        energy, state = eigvals[0], eigvecs[:, 0]
+    else:
+        energy, state = get_ground_state(scipy.sparse.csc_matrix(restricted))
+    expanded = numpy.zeros(2**n_qubits, dtype=complex)
+    expanded[jw_number_indices(particle_number, n_qubits)] = state
+    return energy, expanded

@@ -51,14 +51,19 @@ def main():
             dist.barrier()
             sop.close()
     hub = models.hubbard_jw(2, 4)
-    sop = ShardedPauliOperator(hub, 16, dist=dist, mode='nccl')
-    stats = {}
-    energy, _, residual = lanczos_ground_state(sop, dist, stats=stats)
+    e1 = None
     if rank == 0:
         e1, _ = get_ground_state(LinearQubitOperator(hub, 16))
-        print('lanczos world=%d E=%.12f single-GPU E=%.12f diff=%.2e residual=%.2e matvecs=%d'
-              % (world, energy, e1, abs(energy - e1), residual, stats.get('matvecs', 0)))
-        ok = ok and abs(energy - e1) < 1e-10
+    for mode in ('nccl', 'ce'):
+        sop = ShardedPauliOperator(hub, 16, dist=dist, mode=mode)
+        stats = {}
+        energy, _, residual = lanczos_ground_state(sop, dist, stats=stats)
+        if rank == 0:
+            print('lanczos %s world=%d E=%.12f single-GPU E=%.12f diff=%.2e residual=%.2e matvecs=%d'
+                  % (mode, world, energy, e1, abs(energy - e1), residual, stats.get('matvecs', 0)))
+            ok = ok and abs(energy - e1) < 1e-10
+        sop.close()
+    if rank == 0:
         print('DIST_CHECK', 'PASS' if ok else 'FAIL')
     dist.destroy_process_group()
 

@@ -268,3 +268,25 @@ def test_generate_and_append_random_vectors():
         warnings.simplefilter('ignore', RuntimeWarning)
         full = append_random_vectors(numpy.eye(3, dtype=complex), 2)
     assert full.shape[1] == 3  # more columns than rows cannot be added
+
+
+# ---- sector-restricted ground states (sparse_tools_test.py: jw_get_ground_state_at_particle_number)
+def test_ground_state_at_particle_number_matches_dense_sector():
+    from openfermion_b200.linalg import (jw_get_ground_state_at_particle_number,
+                                         jw_number_restrict_operator, jw_sz_restrict_operator)
+    op = models.hubbard_jw(2, 2, 1.0, 4.0, 0.3, 0.2)
+    csc = qubit_operator_sparse(op, 8)
+    dense = _dense(op, 8)
+    for particles in (0, 1, 2, 4, 8):
+        idx = [i for i in range(256) if bin(i).count('1') == particles]
+        want = numpy.linalg.eigvalsh(dense[numpy.ix_(idx, idx)])[0]
+        energy, state = jw_get_ground_state_at_particle_number(csc, particles)
+        assert abs(energy - want) < 1e-10
+        assert state.shape == (256,) and abs(numpy.linalg.norm(state) - 1) < 1e-10
+        assert abs(numpy.vdot(state, dense @ state) - want) < 1e-9
+    restricted = jw_number_restrict_operator(csc, 4)
+    assert restricted.shape == (70, 70)
+    sz0 = jw_sz_restrict_operator(csc, 0.0, n_electrons=4)
+    assert sz0.shape == (36, 36)
+    lowest_sz0 = numpy.linalg.eigvalsh(sz0.toarray())[0]
+    assert lowest_sz0 >= numpy.linalg.eigvalsh(restricted.toarray())[0] - 1e-10

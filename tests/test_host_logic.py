@@ -216,3 +216,44 @@ def test_linalg_api_surface_and_errors():
     assert len(par.linear_operators) == len(par.qubit_operator_groups)
     assert isinstance(linalg.generate_linear_qubit_operator(QubitOperator('X0')), linalg.LinearQubitOperator)
     assert linalg.inner_product(numpy.array([1j, 0]), numpy.array([1j, 0])) == 1
+
+
+# ---- sector helpers -------------------------------------------------------------
+def test_jw_sector_indices_definitions():
+    from openfermion_b200.linalg import jw_number_indices, jw_sz_indices
+    for n_qubits in (4, 6):
+        for k in range(n_qubits + 1):
+            got = jw_number_indices(k, n_qubits)
+            want = [i for i in range(2**n_qubits) if bin(i).count('1') == k]
+            assert sorted(got) == want and len(set(got)) == len(got)
+    assert jw_number_indices(2, 4) == [3, 5, 9, 6, 10, 12]  # the reference's combination order
+
+    def sz_of(index, n_qubits):
+        up = sum((index >> (n_qubits - 1 - 2 * i)) & 1 for i in range(n_qubits // 2))
+        down = sum((index >> (n_qubits - 2 - 2 * i)) & 1 for i in range(n_qubits // 2))
+        return (up - down) / 2.0, up + down
+
+    for sz in (-1.0, -0.5, 0.0, 0.5, 1.0):
+        got = jw_sz_indices(sz, 6)
+        want = [i for i in range(64) if sz_of(i, 6)[0] == sz]
+        assert sorted(got) == want and len(set(got)) == len(got)
+    got = jw_sz_indices(0.5, 6, n_electrons=3)
+    assert sorted(got) == [i for i in range(64) if sz_of(i, 6) == (0.5, 3)]
+    with pytest.raises(ValueError):
+        jw_sz_indices(0.5, 5)
+    with pytest.raises(ValueError):
+        jw_sz_indices(0.25, 4)
+    with pytest.raises(ValueError):
+        jw_sz_indices(0.5, 4, n_electrons=2)
+
+
+@pytest.mark.needs_reference
+def test_jw_sector_indices_match_reference_order():
+    import ref_shim
+    ref_shim.load()
+    from openfermion.linalg.sparse_tools import jw_number_indices as ref_n, jw_sz_indices as ref_sz
+    from openfermion_b200.linalg import jw_number_indices, jw_sz_indices
+    assert jw_number_indices(3, 7) == ref_n(3, 7)
+    for sz in (-1.5, -1.0, 0.0, 0.5, 1.0):
+        assert jw_sz_indices(sz, 8) == ref_sz(sz, 8)
+    assert jw_sz_indices(-1.0, 8, n_electrons=4) == ref_sz(-1.0, 8, n_electrons=4)
