@@ -104,12 +104,15 @@ __device__ __forceinline__ void apply_class_dyn(uint32_t w, double a, const doub
 
 // all class runs of one segment from one coefficient table
 template <bool Z32, bool IMAG>
-__device__ __forceinline__ void segment_pass(const TermZC *tab, const Segment &sd, uint32_t j_lo,
-                                             uint32_t base_hi, const double2 (&v)[R8],
-                                             double (&ar)[R8], double (&ai)[R8]) {
-    const uint32_t runs = (sd.kind_count >> 24) & 0xfu;
-    uint64_t cnts = sd.cnts;
-    uint32_t ids = sd.ids;
+__device__ __forceinline__ void segment_pass(const TermZC *tab, uint32_t runs, uint64_t cnts,
+                                             uint32_t ids, uint32_t j_lo, uint32_t base_hi,
+                                             const double2 (&v)[R8], double (&ar)[R8],
+                                             double (&ai)[R8]) {
+    if (runs == 1) {  // the common case: no run bookkeeping at all
+        const double a = run_sum<Z32>(tab, (uint32_t)cnts, j_lo, base_hi);
+        apply_class_dyn<IMAG>(ids, a, v, ar, ai);
+        return;
+    }
 #pragma unroll 1
     for (uint32_t k = 0; k < runs; ++k) {
         const uint32_t cnt = (uint32_t)cnts & 0xffu;
@@ -121,12 +124,12 @@ __device__ __forceinline__ void segment_pass(const TermZC *tab, const Segment &s
     }
 }
 
-// &base[index] with one IMAD.WIDE (the compiler otherwise shares the multiply and pays a
-// 64-bit add per amplitude)
-__device__ __forceinline__ const double2 *amp_ptr(const double2 *base, uint32_t index) {
-    const double2 *p;
-    asm("mad.wide.u32 %0, %1, 16, %2;" : "=l"(p) : "r"(index), "l"(base));
-    return p;
+// The 8 input amplitudes of a thread for one segment.  (A variant that computes one address
+// and dispatches on the class bits of x to issue the loads with compile-time offsets was
+// measured 8 % slower: the branch keeps the loads from being issued early.)
+__device__ __forceinline__ void load_tile(const double2 *__restrict__ vin, uint32_t jx, double2 (&v)[R8]) {
+#pragma unroll
+    for (int r = 0; r < R8; ++r) v[r] = vin[(size_t)(jx ^ (uint32_t)(r << CLASS_SHIFT))];
 }
 
 // Shared-memory stage of one chunk: segment descriptors and both coefficient tables.
@@ -160,7 +163,7 @@ __device__ __forceinline__ void stage_chunk(StageBuf &b, const Chunk ck,
     cp_async_commit();
 }
 
-template <bool Z32, bool EXPECT>
+template <bool Z32, bool EXPECT, bool HAS_IMAG>
 __global__ void __launch_bounds__(BLOCK, OFB_APPLY_MIN_CTAS)
 k_apply8(const double2 *__restrict__ vin, double2 *__restrict__ vout,
          const Chunk *__restrict__ chunks, uint32_t c0, uint32_t c1,
@@ -189,11 +192,11 @@ k_apply8(const double2 *__restrict__ vin, double2 *__restrict__ vout,
 
     Chunk cur = chunks[c0];
     Chunk nxt = (c0 + 1 < c1) ? chunks[c0 + 1] : cur;
-    stage_chunk(sbuf[0], cur, segs, zc_re, zc_im, has_imag);
+    stage_chunk(sbuf[0], cur, segs, zc_re, zc_im, HAS_IMAG ? 1 : 0);
     for (uint32_t c = c0; c < c1; ++c) {
         Chunk after = nxt;
         if (c + 1 < c1) {
-            stage_chunk(sbuf[(c + 1 - c0) & 1], nxt, segs, zc_re, zc_im, has_imag);
+            stage_chunk(sbuf[(c + 1 - c0) & 1], nxt, segs, zc_re, zc_im, HAS_IMAG ? 1 : 0);
             if (c + 2 < c1) after = chunks[c + 2];
             cp_async_wait<1>();
         } else {
@@ -203,15 +206,24 @@ k_apply8(const double2 *__restrict__ vin, double2 *__restrict__ vout,
         const StageBuf &b = sbuf[(c - c0) & 1];
         const uint32_t lo = max(cur.seg_begin, s0), hi = min(cur.seg_begin + cur.seg_count, s1);
         for (uint32_t s = lo; s < hi; ++s) {
-            const Segment sd = b.segs[s - cur.seg_begin];
-            const uint32_t jx = j0 ^ ((uint32_t)sd.x & xmask_local);
-            const uint32_t kind = sd.kind_count >> 30;
-            const uint32_t tl = sd.begin - cur.term_begin;
+            const Segment &sd = b.segs[s - cur.seg_begin];
+            const uint32_t kind_runs = sd.kind_runs;
+            const uint32_t ids = sd.ids;
+            const uint64_t cnts = sd.cnts;
+            const uint32_t tl = sd.rel_begin;
+            const uint32_t jx = j0 ^ (sd.x_lo & xmask_local);
+            const uint32_t runs = kind_runs & 0xfu;
             double2 v[R8];
-#pragma unroll
-            for (int r = 0; r < R8; ++r) v[r] = *amp_ptr(vin, jx ^ (uint32_t)(r << CLASS_SHIFT));
-            if (kind != KIND_IMAG) segment_pass<Z32, false>(b.re + tl, sd, j_lo, base_hi, v, ar, ai);
-            if (kind != KIND_REAL) segment_pass<Z32, true>(b.im + tl, sd, j_lo, base_hi, v, ar, ai);
+            load_tile(vin, jx, v);
+            if (!HAS_IMAG) {
+                segment_pass<Z32, false>(b.re + tl, runs, cnts, ids, j_lo, base_hi, v, ar, ai);
+            } else {
+                const uint32_t kind = kind_runs >> 30;
+                if (kind != KIND_IMAG)
+                    segment_pass<Z32, false>(b.re + tl, runs, cnts, ids, j_lo, base_hi, v, ar, ai);
+                if (kind != KIND_REAL)
+                    segment_pass<Z32, true>(b.im + tl, runs, cnts, ids, j_lo, base_hi, v, ar, ai);
+            }
         }
         __syncthreads();  // everyone is done with this buffer before it is refilled
         cur = nxt;
@@ -258,7 +270,8 @@ k_apply8(const double2 *__restrict__ vin, double2 *__restrict__ vout,
 template <bool EXPECT>
 __global__ void __launch_bounds__(BLOCK)
 k_apply1(const double2 *__restrict__ vin, double2 *__restrict__ vout,
-         const Segment *__restrict__ segs, uint32_t s0, uint32_t s1,
+         const Segment *__restrict__ segs, const uint32_t *__restrict__ seg_term_begin,
+         uint32_t s0, uint32_t s1,
          const TermZC *__restrict__ zc_re, const TermZC *__restrict__ zc_im, uint32_t dim,
          uint64_t index_base, int accumulate, double2 *__restrict__ partials) {
     const uint32_t j = blockIdx.x * BLOCK + threadIdx.x;
@@ -272,8 +285,8 @@ k_apply1(const double2 *__restrict__ vin, double2 *__restrict__ vout,
     }
     for (uint32_t s = s0; s < s1; ++s) {
         const Segment sd = segs[s];
-        const uint32_t kind = sd.kind_count >> 30;
-        const uint32_t tb = sd.begin, te = sd.begin + (sd.kind_count & 0xffffffu);
+        const uint32_t kind = sd.kind_runs >> 30;
+        const uint32_t tb = seg_term_begin[s], te = tb + ((sd.kind_runs >> 8) & 0xffffu);
         const double2 v = valid ? vin[j ^ ((uint32_t)sd.x & (dim - 1))] : make_double2(0.0, 0.0);
         double sr = 0.0, si = 0.0;
         for (uint32_t t = tb; t < te; ++t) {
@@ -358,18 +371,21 @@ static int launch_apply_impl(ofb_plan *p, const void *d_in, void *d_out, int loc
     double2 *out = (double2 *)d_out;
     if (local_bits >= TILE8_BITS) {
         const uint32_t xmask = (uint32_t)(dim - 1);
-        if (p->z_fits32)
-            k_apply8<true, EXPECT><<<(unsigned)blocks, BLOCK, 0, s>>>(
-                in, out, p->d_chunks, c0, c1, p->d_segs, s0, s1, p->d_zc, p->d_zc_im,
-                p->has_imag ? 1 : 0, xmask, index_base, accumulate, partials);
-        else
-            k_apply8<false, EXPECT><<<(unsigned)blocks, BLOCK, 0, s>>>(
-                in, out, p->d_chunks, c0, c1, p->d_segs, s0, s1, p->d_zc, p->d_zc_im,
-                p->has_imag ? 1 : 0, xmask, index_base, accumulate, partials);
+#define OFB_GO(ZZ, II)                                                                         \
+    k_apply8<ZZ, EXPECT, II><<<(unsigned)blocks, BLOCK, 0, s>>>(                               \
+        in, out, p->d_chunks, c0, c1, p->d_segs, s0, s1, p->d_zc, p->d_zc_im, 0, xmask,        \
+        index_base, accumulate, partials)
+        if (p->z_fits32) {
+            if (p->has_imag) OFB_GO(true, true); else OFB_GO(true, false);
+        } else {
+            if (p->has_imag) OFB_GO(false, true); else OFB_GO(false, false);
+        }
+#undef OFB_GO
     } else {
-        k_apply1<EXPECT><<<(unsigned)blocks, BLOCK, 0, s>>>(in, out, p->d_segs, s0, s1, p->d_zc,
-                                                            p->d_zc_im, (uint32_t)dim, index_base,
-                                                            accumulate, partials);
+        k_apply1<EXPECT><<<(unsigned)blocks, BLOCK, 0, s>>>(in, out, p->d_segs, p->d_seg_term_begin,
+                                                            s0, s1, p->d_zc, p->d_zc_im,
+                                                            (uint32_t)dim, index_base, accumulate,
+                                                            partials);
     }
     OFB_LAUNCH_CHECK();
     return OFB_OK;

@@ -51,12 +51,12 @@ struct __align__(16) GroupDesc {  // scatter-form groups of the CSC builder
 constexpr int CLASS_SHIFT = OFB_APPLY_BLOCK_BITS;  // log2(threads per block) of the apply kernel
 constexpr int SEG_MAX_TERMS = 255;
 struct __align__(16) Segment {
-    uint64_t x;
-    uint32_t begin;       // first term of the segment
-    uint32_t kind_count;  // bits 0..23 term count, bits 24..27 number of class runs, 30..31 kind
-    uint64_t cnts;
-    uint32_t ids;
-    uint32_t pad;
+    uint32_t x_lo;       // low 32 bits of the x mask (all a device-local index can use)
+    uint32_t rel_begin;  // first term, relative to the first term of the segment's chunk
+    uint32_t kind_runs;  // bits 0..3 number of class runs, bits 8..23 term count, 30..31 kind
+    uint32_t ids;        // nibble k = class of run k
+    uint64_t cnts;       // byte k = length of run k
+    uint64_t x;          // full mask (host side, small-state kernel)
 };
 // Staging unit of the apply kernel: consecutive segments whose descriptors and term tables
 // are copied to shared memory together (double buffered with cp.async).
@@ -103,6 +103,7 @@ struct ofb_plan {
     bool has_imag = false;  // some group has a non-real phased coefficient
     ofb::Chunk *d_chunks = nullptr;
     ofb::Segment *d_segs = nullptr;
+    uint32_t *d_seg_term_begin = nullptr;  // absolute first term of each segment (small-state kernel)
     ofb::TermZC *d_zc = nullptr;     // (z, Re c) in segment/class order
     ofb::TermZC *d_zc_im = nullptr;  // (z, Im c) in the same order
     ofb::GroupDesc *d_groups = nullptr;  // scatter-form groups (CSC)

@@ -347,7 +347,8 @@ int ofb_plan_create(int n_qubits, int64_t n_terms, const uint64_t *x_mask, const
             // a chunk of a class-sorted list is still class-sorted
             Segment sd{};
             sd.x = p->h_group_x[g];
-            sd.begin = (uint32_t)zc_re.size();
+            sd.x_lo = (uint32_t)p->h_group_x[g];
+            sd.rel_begin = (uint32_t)zc_re.size();  // absolute for now; made chunk-relative below
             uint64_t cnts = 0;
             uint32_t ids = 0, runs = 0;
             int last_cls = -1;
@@ -363,24 +364,27 @@ int ofb_plan_create(int n_qubits, int64_t n_terms, const uint64_t *x_mask, const
                 zc_re.push_back(TermZC{z_mask[order[k]], gr[k]});
                 zc_im.push_back(TermZC{z_mask[order[k]], gi[k]});
             }
-            sd.kind_count = (uint32_t)(end - pos) | (runs << 24) | (kind << 30);
+            sd.kind_runs = runs | ((uint32_t)(end - pos) << 8) | (kind << 30);
             sd.cnts = cnts;
             sd.ids = ids;
             segs.push_back(sd);
         }
     }
     p->h_seg_begin[p->n_groups] = (uint32_t)segs.size();
+    std::vector<uint32_t> seg_term_begin(segs.size());
+    for (size_t sidx = 0; sidx < segs.size(); ++sidx) seg_term_begin[sidx] = segs[sidx].rel_begin;
     // chunks: runs of <= CHUNK_MAX_SEGS segments holding <= CHUNK_MAX_TERMS terms
     std::vector<Chunk> chunks;
     p->h_chunk_of_seg.assign(segs.size(), 0);
     for (size_t sidx = 0; sidx < segs.size(); ++sidx) {
-        uint32_t cnt = segs[sidx].kind_count & 0xffffffu;
-        if ((segs[sidx].kind_count >> 30) != KIND_REAL) p->has_imag = true;
+        uint32_t cnt = (segs[sidx].kind_runs >> 8) & 0xffffu;
+        if ((segs[sidx].kind_runs >> 30) != KIND_REAL) p->has_imag = true;
         if (chunks.empty() || chunks.back().seg_count >= (uint32_t)CHUNK_MAX_SEGS ||
             chunks.back().term_count + cnt > (uint32_t)CHUNK_MAX_TERMS)
-            chunks.push_back(Chunk{(uint32_t)sidx, 0, segs[sidx].begin, 0});
+            chunks.push_back(Chunk{(uint32_t)sidx, 0, segs[sidx].rel_begin, 0});
         chunks.back().seg_count += 1;
         chunks.back().term_count += cnt;
+        segs[sidx].rel_begin -= chunks.back().term_begin;
         p->h_chunk_of_seg[sidx] = (uint32_t)chunks.size() - 1;
     }
     p->n_chunks = (int64_t)chunks.size();
@@ -392,6 +396,7 @@ int ofb_plan_create(int n_qubits, int64_t n_terms, const uint64_t *x_mask, const
         groups[g] = GroupDesc{p->h_group_x[g], p->h_group_begin[g],
                               p->h_group_begin[g + 1] - p->h_group_begin[g]};
     if ((rc = upload(&p->d_chunks, chunks)) || (rc = upload(&p->d_segs, segs)) ||
+        (rc = upload(&p->d_seg_term_begin, seg_term_begin)) ||
         (rc = upload(&p->d_zc, zc_re)) ||
         (rc = upload(&p->d_zc_im, zc_im)) || (rc = upload(&p->d_groups, groups))) {
         ofb_plan_destroy(p);
@@ -445,6 +450,7 @@ int ofb_plan_destroy(ofb_plan *p) {
     cudaSetDevice(p->device);
     cudaFree(p->d_groups);
     cudaFree(p->d_segs);
+    cudaFree(p->d_seg_term_begin);
     cudaFree(p->d_chunks);
     cudaFree(p->d_zc);
     cudaFree(p->d_zc_im);
