@@ -178,7 +178,8 @@ class Davidson:
     def _capacity(self, dim, n_lowest):
         want = self.options.max_subspace + n_lowest
         free = _lib.c_size_t()
-        _lib.call('ofb_device_info', _lib.c_int(0), None, None, _lib.ctypes.byref(free), None, None)
+        device = getattr(getattr(self._device_operator, 'plan', None), 'device', 0)
+        _lib.call('ofb_device_info', _lib.c_int(device), None, None, _lib.ctypes.byref(free), None, None)
         fit = int(0.45 * free.value // (dim * C128)) - 2 * n_lowest - 2
         return max(min(want, fit), n_lowest + 2)
 
@@ -286,10 +287,7 @@ class Davidson:
 
     @staticmethod
     def _max_imag(dim, column_ptr):
-        tmp = _lib.DeviceBuffer(dim * C128)
-        krylov.copy(dim, column_ptr, tmp.ptr)
-        full = krylov.download(dim, tmp.ptr)
-        tmp.free()
+        full = krylov.download(dim, column_ptr)
         return float(numpy.max(numpy.abs(full.imag))) if dim else 0.0
 
     def _iterate(self, op, n_lowest, V, MV, TV, TMV, R, vmv, vmv_valid):

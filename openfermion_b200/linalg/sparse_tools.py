@@ -68,6 +68,20 @@ def _tensor_fermion_terms(operator):
     return accumulated
 
 
+def _diagonal_coulomb_fermion_terms(operator):
+    """constant + sum_pq T_pq p^ q + sum_pq V_pq p^ p q^ q in the reference's order
+    (transforms/opconversions/conversions.py:124-132)."""
+    one_body = numpy.asarray(operator.one_body)
+    two_body = numpy.asarray(operator.two_body)
+    n = one_body.shape[0]
+    out = ops.FermionOperator()
+    out += ops.FermionOperator((), operator.constant)
+    for p, q in itertools.product(range(n), repeat=2):
+        out += ops.FermionOperator(((p, 1), (q, 0)), one_body[p, q])
+        out += ops.FermionOperator(((p, 1), (p, 0), (q, 1), (q, 0)), two_body[p, q])
+    return out
+
+
 def _to_fermion_operator(operator):
     try:  # upstream converter when OpenFermion itself is installed
         from openfermion.transforms.opconversions import get_fermion_operator
@@ -76,6 +90,8 @@ def _to_fermion_operator(operator):
         pass
     if hasattr(operator, 'n_body_tensors'):
         return _tensor_fermion_terms(operator)
+    if all(hasattr(operator, name) for name in ('one_body', 'two_body', 'constant')):
+        return _diagonal_coulomb_fermion_terms(operator)
     raise TypeError('{} cannot be converted to FermionOperator'.format(type(operator)))
 
 
@@ -83,7 +99,8 @@ def get_sparse_operator(operator, n_qubits=None, trunc=None, hbar=1.0):
     """Type dispatch of sparse_tools.py:1249-1279.  Boson / quadrature operators are outside
     the Pauli-sum path and are passed to upstream if present."""
     names = {c.__name__ for c in type(operator).__mro__}
-    if names & {'DiagonalCoulombHamiltonian', 'PolynomialTensor'} or hasattr(operator, 'n_body_tensors'):
+    if (names & {'DiagonalCoulombHamiltonian', 'PolynomialTensor'} or hasattr(operator, 'n_body_tensors')
+            or all(hasattr(operator, name) for name in ('one_body', 'two_body', 'constant'))):
         return jordan_wigner_sparse(_to_fermion_operator(operator))
     if ops.is_fermion_operator(operator):
         return jordan_wigner_sparse(operator, n_qubits)

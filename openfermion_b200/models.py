@@ -339,3 +339,13 @@ def molecular_hamiltonian(nuclear_repulsion, one_body_integrals, two_body_integr
     (chem/molecular_data.py:1021-1039)."""
     one, two = spin_orbital_tensors(one_body_integrals, two_body_integrals)
     return InteractionTensor(nuclear_repulsion, one, 0.5 * two)
+
+
+class DiagonalCoulomb:
+    """Minimal stand-in for the reference's DiagonalCoulombHamiltonian
+    (ops/representations/diagonal_coulomb_hamiltonian.py): sum T_pq p^ q + sum V_pq n_p n_q + c."""
+
+    def __init__(self, one_body, two_body, constant=0.0):
+        self.one_body = numpy.asarray(one_body)
+        self.two_body = numpy.asarray(two_body)
+        self.constant = constant

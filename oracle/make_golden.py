@@ -134,6 +134,16 @@ def fermion_cases():
         cases[name + '/indices'] = ref_csc.indices
         cases[name + '/data'] = ref_csc.data
         names.append(name)
+    # DiagonalCoulombHamiltonian through get_sparse_operator (sparse_tools_test.py:1876-1890)
+    from openfermion.testing.testing_utils import random_diagonal_coulomb_hamiltonian
+    dch = random_diagonal_coulomb_hamiltonian(5, real=False, seed=3)
+    ref_csc = get_sparse_operator(dch)
+    cases['dch/one_body'] = dch.one_body
+    cases['dch/two_body'] = dch.two_body
+    cases['dch/constant'] = numpy.array(dch.constant)
+    cases['dch/indptr'] = ref_csc.indptr
+    cases['dch/indices'] = ref_csc.indices
+    cases['dch/data'] = ref_csc.data
     cases['names'] = numpy.array(names, dtype=str)
     numpy.savez_compressed(os.path.join(GOLDEN, 'fermion_cases.npz'), **cases)
     print('fermion_cases:', len(names), 'cases')

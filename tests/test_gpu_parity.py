@@ -407,3 +407,11 @@ def test_shards_of_states_beyond_32_qubits(n, local_bits):
     # accumulate flag: a second application doubles the result
     plan.apply_groups_device(d_in.ptr, d_out.ptr, local_bits, base, 0, plan.n_groups, 1)
     assert helpers.close(krylov.download(ld, d_out.ptr), 2 * want, 1e-13)
+
+
+def test_diagonal_coulomb_hamiltonian_route():
+    # sparse_tools_test.py:1876-1890: get_sparse_operator(DiagonalCoulombHamiltonian)
+    data = helpers.golden('fermion_cases.npz')
+    dch = models.DiagonalCoulomb(data['dch/one_body'], data['dch/two_body'], complex(data['dch/constant']).real)
+    mat = get_sparse_operator(dch)
+    helpers.assert_csc_matches(mat, data['dch/indptr'], data['dch/indices'], data['dch/data'], RTOL)
