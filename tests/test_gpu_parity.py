@@ -415,3 +415,73 @@ def test_diagonal_coulomb_hamiltonian_route():
     dch = models.DiagonalCoulomb(data['dch/one_body'], data['dch/two_body'], complex(data['dch/constant']).real)
     mat = get_sparse_operator(dch)
     helpers.assert_csc_matches(mat, data['dch/indptr'], data['dch/indices'], data['dch/data'], RTOL)
+
+
+# ---- BASELINE.json full sizes: size-independent properties, device-resident ----------------------
+def _device_random(n, seed):
+    from openfermion_b200 import _lib
+    from openfermion_b200.linalg import krylov
+    dim = 1 << n
+    buf = _lib.DeviceBuffer(dim * 16)
+    krylov.fill_random(dim, seed, False, buf.ptr)
+    krylov.scal(dim, 1.0 / krylov.nrm2(dim, buf.ptr), buf.ptr)
+    return buf
+
+
+def test_full_size_molecular_28_qubits_properties():
+    """Config 4 at full size (T = 88 495, 2^28 amplitudes): Hermiticity, linearity and the
+    fused expectation against K1 + dot, all on device-resident vectors."""
+    from openfermion_b200 import _lib
+    from openfermion_b200.linalg import krylov
+    n = 28
+    dim = 1 << n
+    op = models.molecular_jw(14, seed=1234)
+    plan = LinearQubitOperator(op, n).plan
+    assert (plan.n_terms, plan.n_groups) == (88495, 10466)
+    u, v = _device_random(n, 1), _device_random(n, 2)
+    hu, hv = _lib.DeviceBuffer(dim * 16), _lib.DeviceBuffer(dim * 16)
+    plan.apply_device(u.ptr, hu.ptr)
+    plan.apply_device(v.ptr, hv.ptr)
+    scale = float(numpy.sum(numpy.abs(op.coeff)))
+    uhv, vhu = krylov.dotc(dim, u.ptr, hv.ptr), krylov.dotc(dim, v.ptr, hu.ptr)
+    assert abs(uhv - numpy.conj(vhu)) <= 1e-12 * scale
+    e_u = krylov.dotc(dim, u.ptr, hu.ptr)
+    assert abs(e_u.imag) <= 1e-12 * scale
+    assert abs(plan.expectation_device(u.ptr) - e_u) <= 1e-12 * scale
+    # linearity: H(0.3 u - 1.7i v) = 0.3 Hu - 1.7i Hv   (re-uses u and hu as work space)
+    a, b = 0.3, -1.7j
+    krylov.scal(dim, a, u.ptr)
+    krylov.axpy(dim, b, v.ptr, u.ptr)
+    krylov.scal(dim, a, hu.ptr)
+    krylov.axpy(dim, b, hv.ptr, hu.ptr)      # hu <- expected
+    plan.apply_device(u.ptr, hv.ptr)          # hv <- H(combination)
+    krylov.axpy(dim, -1.0, hu.ptr, hv.ptr)
+    assert krylov.maxabs(dim, hv.ptr) <= 1e-12 * scale
+
+
+def test_maximum_single_gpu_size_32_qubits_columns():
+    """2^32 amplitudes on one GPU (the 32-bit local index boundary): H e_c for basis states c
+    near both ends of the index range must equal the column of H computed with Python
+    integers -- right rows, right values, nothing written anywhere else."""
+    from openfermion_b200 import _lib
+    from openfermion_b200.linalg import krylov
+    n = 32
+    dim = 1 << n
+    op = models.hubbard_jw(4, 4)
+    x, z, c = compiler.compile_qubit_operator(op, n)
+    plan = LinearQubitOperator(op, n).plan
+    d_in, d_out = _lib.DeviceBuffer(dim * 16), _lib.DeviceBuffer(dim * 16)
+    one = numpy.array([1.0 + 0.0j])
+    for col in (dim - 1, (1 << 31) + 12345, 0x5A5A5A5A, 7):
+        _lib.call('ofb_memset', _lib.c_void_p(d_in.ptr), _lib.c_int(0), _lib.c_size_t(dim * 16), None)
+        krylov.upload(one, d_in.ptr + col * 16)
+        plan.apply_device(d_in.ptr, d_out.ptr)
+        want = {}
+        for xt, zt, ct in zip(x.tolist(), z.tolist(), c.tolist()):
+            value = ct * (1j) ** bin(xt & zt).count('1') * (-1) ** bin(col & zt).count('1')
+            want[col ^ xt] = want.get(col ^ xt, 0) + value
+        for row, value in want.items():
+            got = krylov.download(1, d_out.ptr + row * 16)[0]
+            assert abs(got - value) <= 1e-13 * max(1.0, abs(value)), (col, row)
+        norm2 = krylov.dotc(dim, d_out.ptr, d_out.ptr).real
+        assert abs(norm2 - sum(abs(v) ** 2 for v in want.values())) <= 1e-10 * max(norm2, 1.0)
