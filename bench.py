@@ -285,6 +285,35 @@ def run_single(args):
         except Exception:
             pass
     cpu = None if args.no_cpu_baseline else cpu_baseline_sample(op, n)
+    # same-workload base for the multi-GPU lines (Hubbard 4x4, 32 qubits on ONE GPU)
+    aux = None
+    if args.aux_hubbard32 and n == 28:
+        try:
+            d_in.free()
+            d_out.free()
+            plan.close()
+            from openfermion_b200 import models
+            hub = LinearQubitOperator(models.hubbard_jw(4, 4), 32)
+            hdim = 1 << 32
+            h_in, h_out = _lib.DeviceBuffer(hdim * 16), _lib.DeviceBuffer(hdim * 16)
+            krylov.fill_random(hdim, 7, False, h_in.ptr)
+            for _ in range(2):
+                hub.plan.apply_device(h_in.ptr, h_out.ptr)
+            _lib.call('ofb_event_record', ev[0], vp(None))
+            for _ in range(3):
+                hub.plan.apply_device(h_in.ptr, h_out.ptr)
+            _lib.call('ofb_event_record', ev[1], vp(None))
+            _lib.call('ofb_event_sync', ev[1])
+            hms = ctypes.c_float()
+            _lib.call('ofb_event_elapsed_ms', ev[0], ev[1], ctypes.byref(hms))
+            aux = {'workload': 'Fermi-Hubbard 4x4 spinful JW, 32 qubits, ONE GPU (strong-scaling base of the --gpus N lines)',
+                   'ms_per_step': hms.value / 3, 'value': hub.plan.n_terms * float(hdim) * 3 / (hms.value / 1e3),
+                   'unit': UNIT, 'terms': hub.plan.n_terms, 'x_groups': hub.plan.n_groups}
+            h_in.free()
+            h_out.free()
+        except Exception as exc:  # e.g. not enough memory on a shared box
+            aux = {'error': str(exc)[:200]}
+    dram = (traffic / (seconds / args.steps) / 1e9) if traffic else None
     line = {
         'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': 1, 'steps': args.steps,
         'warmup': args.warmup, 'ms_per_step': ms.value / args.steps, 'higher_is_better': True,
@@ -300,8 +329,14 @@ def run_single(args):
         'roofline': {'bound': 'hbm', 'achieved': achieved, 'peak': peak, 'unit': 'GB/s',
                      'frac': achieved / peak, 'traffic': traffic, 'peak_source': peak_src,
                      'kernel': 'k_apply', 'algorithmic_bytes_per_launch': alg_bytes,
-                     'frac_of_8TBs_nominal': achieved / 8000.0},
+                     'frac_of_8TBs_nominal': achieved / 8000.0,
+                     'dram_achieved': dram, 'dram_frac': (dram / peak) if dram else None,
+                     'note': 'x-groups run in ascending x, so the input tile is re-read through L1/L2: '
+                             'real DRAM traffic (traffic, ncu) is a fraction of the algorithmic bytes and '
+                             'frac exceeds 1; the binding limits are SM issue rate and the L1 data pipe '
+                             '(DESIGN.md section 4, profiles/README.md)'},
         'cpu_baseline': cpu,
+        'aux': aux,
     }
     print(json.dumps(line))
 
@@ -315,6 +350,8 @@ def main():
     ap.add_argument('--qubits', type=int, default=28, help='N=1 workload size (even)')
     ap.add_argument('--e2e-steps', type=int, default=2)
     ap.add_argument('--no-cpu-baseline', action='store_true')
+    ap.add_argument('--no-aux', dest='aux_hubbard32', action='store_false',
+                    help='skip the one-GPU 32-qubit Hubbard measurement appended to the N=1 line')
     ap.add_argument('--reference-qubits', type=int, default=26,
                     help='state size of the bounded sample of the --impl reference arm')
     ap.add_argument('--dist-qubits', type=int, default=32, help='N>1 workload size (Hubbard)')

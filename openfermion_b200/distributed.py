@@ -387,6 +387,23 @@ def lanczos_ground_state(operator, dist, group=None, tol=1e-10, krylov_dim=None,
 # ----------------------------------------------------------------------------
 # bench entry for N > 1 (called by bench.py under torchrun)
 # ----------------------------------------------------------------------------
+def one_gpu_base(n_qubits):
+    """One-GPU measurement of the same Hubbard workload (profiles/sweep_r01.jsonl), so that the
+    strong-scaling base of a --gpus N line is explicit (the N = 1 bench line is a different
+    workload: BASELINE.json quotes the metric at 28 qubits on 1 GPU and 32 qubits on 2/4/8)."""
+    path = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), 'profiles',
+                        'sweep_r01.jsonl')
+    try:
+        for raw in open(path):
+            rec = json.loads(raw)
+            if rec.get('n_qubits') == n_qubits and rec.get('workload', '').startswith('hubbard'):
+                return {'ms_per_step': rec['ms_per_matvec'], 'value': rec['term_amp_per_s'],
+                        'source': 'profiles/sweep_r01.jsonl'}
+    except Exception:
+        pass
+    return None
+
+
 def bench_main(args, metric, unit, clock_sampler_cls, measured_peak):
     import torch
     import torch.distributed as dist
@@ -520,6 +537,7 @@ def bench_main(args, metric, unit, clock_sampler_cls, measured_peak):
                        'exchange_bytes_per_rank_per_step': layout.exchange_bytes_per_matvec() if mode in ('nccl', 'ce') else None,
                        'l2_policy': 'inputs exceed L2 (%.1f GB per shard)' % (dim_local * 16 / 1e9),
                        'timing': 'CUDA events, max over ranks', 'expectation_check': [e.real, e.imag],
+                       'one_gpu_same_workload': one_gpu_base(n),
                        'diagnose': diag},
             'clocks': clocks,
             'e2e': {'value': T * dim * e2e_steps / e2e_s, 'unit': unit,
