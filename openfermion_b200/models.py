@@ -104,32 +104,87 @@ def _mul_strings(x1, z1, c1, x2, z2, c2):
     return x3, z3, c1 * c2 * _I_POW[k % 4]
 
 
-def jordan_wigner_products(modes, kinds, coeffs, n_qubits):
-    """JW image of sum_t coeffs[t] * prod_j ladder(modes[t, j], kinds[j]) as a MaskOperator.
+def jw_tables(n_qubits):
+    """Per mode p the two Pauli strings of its ladder operators under Jordan-Wigner:
+    A = X_p Z_<p and B = Y_p Z_<p, with a_p^(dagger) = (A -/+ ... ) i.e. 1/2 (A -+ i B)."""
+    one = numpy.uint64(1)
+    p = numpy.arange(n_qubits, dtype=numpy.uint64)
+    bit = one << p
+    low = bit - one
+    return bit, low, bit, low | bit
+
+
+def _bk_sets(index, n_qubits):
+    """Fenwick-tree update / occupation / parity sets of the Bravyi-Kitaev transform
+    (transforms/opconversions/bravyi_kitaev.py:54-99), as bit masks."""
+    update = 0
+    i = index + 1
+    i += i & -i
+    while i <= n_qubits:
+        update |= 1 << (i - 1)
+        i += i & -i
+    occupation = 1 << index
+    i = index + 1
+    parent = i & (i - 1)
+    i -= 1
+    while i != parent:
+        occupation |= 1 << (i - 1)
+        i &= i - 1
+    parity = 0
+    i = index
+    while i > 0:
+        parity |= 1 << (i - 1)
+        i &= i - 1
+    return update, occupation, parity
+
+
+def bk_tables(n_qubits):
+    """Bravyi-Kitaev ladder strings (bravyi_kitaev.py:178-212): A = X_{U+j} Z_P,
+    B = Y_j X_U Z_{(P^O)-j}; a_j^dagger = 1/2 (A - i B), a_j = 1/2 (A + i B)."""
+    xa, za, xb, zb = [], [], [], []
+    for j in range(n_qubits):
+        update, occupation, parity = _bk_sets(j, n_qubits)
+        bit = 1 << j
+        xa.append(update | bit)
+        za.append(parity)
+        xb.append(update | bit)
+        zb.append(((parity ^ occupation) & ~bit) | bit)
+    as_u64 = lambda v: numpy.array(v, dtype=numpy.uint64)  # noqa: E731
+    return as_u64(xa), as_u64(za), as_u64(xb), as_u64(zb)
+
+
+def ladder_products(modes, kinds, coeffs, tables):
+    """Qubit image of sum_t coeffs[t] * prod_j ladder(modes[t, j], kinds[j]) for an encoding
+    given by its per-mode string tables (jw_tables / bk_tables).
 
     modes: int array (T, k); kinds: length-k tuple of 1 (raising) / 0 (lowering).
+    Returns the un-collected (x, z, coefficient) arrays of all 2^k expansions.
     """
+    xa, za, xb, zb = tables
     modes = numpy.asarray(modes, dtype=numpy.int64).reshape(len(coeffs), -1)
     coeffs = numpy.asarray(coeffs, dtype=numpy.complex128)
     k = modes.shape[1]
-    one = numpy.uint64(1)
     xs, zs, cs = [], [], []
     for choice in itertools.product((0, 1), repeat=k):
         x = numpy.zeros(len(coeffs), dtype=numpy.uint64)
         z = numpy.zeros(len(coeffs), dtype=numpy.uint64)
         c = coeffs.copy()
         for j in range(k):
-            bit = one << modes[:, j].astype(numpy.uint64)
-            low = bit - one
+            m = modes[:, j]
             if choice[j] == 0:
-                xj, zj, cj = bit, low, 0.5
+                xj, zj, cj = xa[m], za[m], 0.5
             else:
-                xj, zj, cj = bit, low | bit, (-0.5j if kinds[j] else 0.5j)
+                xj, zj, cj = xb[m], zb[m], (-0.5j if kinds[j] else 0.5j)
             x, z, c = _mul_strings(x, z, c, xj, zj, numpy.complex128(cj))
         xs.append(x)
         zs.append(z)
         cs.append(c)
     return numpy.concatenate(xs), numpy.concatenate(zs), numpy.concatenate(cs)
+
+
+def jordan_wigner_products(modes, kinds, coeffs, n_qubits):
+    """JW image of sum_t coeffs[t] * prod_j ladder(modes[t, j], kinds[j])."""
+    return ladder_products(modes, kinds, coeffs, jw_tables(n_qubits))
 
 
 def _collect(n_qubits, pieces, tol=EQ_TOLERANCE):
@@ -193,23 +248,33 @@ def hubbard_fermion_terms(x_dimension, y_dimension, tunneling, coulomb, chemical
     return out
 
 
-def _jw_of_term_list(term_list, n_qubits):
+def _tables_for(encoding, n_qubits):
+    if encoding in ('jw', 'jordan_wigner'):
+        return jw_tables(n_qubits)
+    if encoding in ('bk', 'bravyi_kitaev'):
+        return bk_tables(n_qubits)
+    raise ValueError('encoding must be jw or bk')
+
+
+def _jw_of_term_list(term_list, n_qubits, encoding='jw'):
+    tables = _tables_for(encoding, n_qubits)
     by_kind = {}
     for modes, kinds, coefficient in term_list:
         by_kind.setdefault(kinds, ([], []))
         by_kind[kinds][0].append(modes)
         by_kind[kinds][1].append(coefficient)
-    pieces = [jordan_wigner_products(m, kinds, c, n_qubits) for kinds, (m, c) in by_kind.items()]
+    pieces = [ladder_products(m, kinds, c, tables) for kinds, (m, c) in by_kind.items()]
     return _collect(n_qubits, pieces)
 
 
 def hubbard_jw(x_dimension, y_dimension, tunneling=1.0, coulomb=4.0, chemical_potential=0.0,
-               magnetic_field=0.0, periodic=True):
-    """jordan_wigner(fermi_hubbard(x, y, t, U)) as a MaskOperator (2*x*y qubits)."""
+               magnetic_field=0.0, periodic=True, encoding='jw'):
+    """jordan_wigner(fermi_hubbard(x, y, t, U)) as a MaskOperator (2*x*y qubits);
+    encoding='bk' gives bravyi_kitaev(...) instead."""
     n_qubits = 2 * x_dimension * y_dimension
     terms = hubbard_fermion_terms(x_dimension, y_dimension, tunneling, coulomb, chemical_potential,
                                   magnetic_field, periodic)
-    return _jw_of_term_list(terms, n_qubits)
+    return _jw_of_term_list(terms, n_qubits, encoding)
 
 
 # ----------------------------------------------------------------------------
@@ -257,29 +322,32 @@ def random_interaction_tensors(n_orbitals, seed=None, dyadic_bits=None):
     return constant, one_spin, two_spin
 
 
-def interaction_operator_jw(constant, one_body, two_body):
+def interaction_operator_jw(constant, one_body, two_body, encoding='jw'):
     """JW of constant + sum h_pq p^ q + sum h_pqrs p^ q^ r s (InteractionOperator convention,
     ops/representations/interaction_operator.py) as a MaskOperator."""
     one_body = numpy.asarray(one_body)
     two_body = numpy.asarray(two_body)
     n_qubits = one_body.shape[0]
+    tables = _tables_for(encoding, n_qubits)
     pieces = []
     if constant:
         pieces.append((numpy.zeros(1, numpy.uint64), numpy.zeros(1, numpy.uint64),
                        numpy.array([constant], dtype=numpy.complex128)))
     idx1 = numpy.argwhere(one_body != 0)
     if len(idx1):
-        pieces.append(jordan_wigner_products(idx1, (1, 0), one_body[tuple(idx1.T)], n_qubits))
+        pieces.append(ladder_products(idx1, (1, 0), one_body[tuple(idx1.T)], tables))
     idx2 = numpy.argwhere(two_body != 0)
     if len(idx2):
-        pieces.append(jordan_wigner_products(idx2, (1, 1, 0, 0), two_body[tuple(idx2.T)], n_qubits))
+        pieces.append(ladder_products(idx2, (1, 1, 0, 0), two_body[tuple(idx2.T)], tables))
     return _collect(n_qubits, pieces)
 
 
-def molecular_jw(n_orbitals, seed=1234, dyadic_bits=None):
+def molecular_jw(n_orbitals, seed=1234, dyadic_bits=None, encoding='jw'):
     """The synthetic molecular-type qubit Hamiltonian of BASELINE.json (2*n_orbitals qubits):
-    jordan_wigner(random_interaction_operator(n_orbitals, expand_spin=True, real=True, seed))."""
-    return interaction_operator_jw(*random_interaction_tensors(n_orbitals, seed, dyadic_bits))
+    jordan_wigner(random_interaction_operator(n_orbitals, expand_spin=True, real=True, seed));
+    encoding='bk' applies bravyi_kitaev to the same fermion operator."""
+    return interaction_operator_jw(*random_interaction_tensors(n_orbitals, seed, dyadic_bits),
+                                   encoding=encoding)
 
 
 def random_pauli_sum(n_qubits, n_terms, seed=0, complex_coefficients=False):

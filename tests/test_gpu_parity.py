@@ -208,6 +208,8 @@ def _state(n, seed):
     ('dense_paulis_complex_n15', lambda: models.random_pauli_sum(15, 300, 3, True)),
     ('dense_paulis_real_n13', lambda: models.random_pauli_sum(13, 500, 4, False)),
     ('hubbard_3x4_n24', lambda: models.hubbard_jw(3, 4)),
+    ('molecular_bk_n16', lambda: models.molecular_jw(8, seed=1234, encoding='bk')),
+    ('hubbard_2x5_bk_n20', lambda: models.hubbard_jw(2, 5, encoding='bk')),
 ])
 def test_matvec_and_expectation_vs_c_oracle(name, builder):
     op = builder()

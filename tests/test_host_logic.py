@@ -147,6 +147,8 @@ def test_dead_fermion_terms_emit_nothing():
     ('hubbard_2x2_mu_h_jw', lambda: models.hubbard_jw(2, 2, 1.0, 4.0, 0.3, 0.2)),
     ('hubbard_2x3_jw', lambda: models.hubbard_jw(2, 3, 1.0, 4.0)),
     ('molecular_8_jw', lambda: models.molecular_jw(4, seed=1234)),
+    ('hubbard_2x2_bk', lambda: models.hubbard_jw(2, 2, 1.0, 4.0, encoding='bk')),
+    ('molecular_6_bk', lambda: models.molecular_jw(3, seed=5, encoding='bk')),
 ])
 def test_generators_reproduce_reference_operators(name, builder):
     data = helpers.golden('qubit_cases.npz')
