@@ -184,6 +184,57 @@ int ofb_vec_drop_imag(int64_t n, void *d_x, void *stream);
 /* deterministic pseudo-random fill in [0,1) (+ i[0,1) unless real_only), counter based */
 int ofb_vec_fill_random(int64_t n, uint64_t seed, int real_only, void *d_x, void *stream);
 
+/* ---- K7: symmetry sectors (particle number / S_z) --------------------------
+ * The reference restricts an operator by materialising the full 2^n x 2^n matrix and slicing it
+ * with numpy.ix_ (linalg/sparse_tools.py:375-423 jw_number_restrict_operator /
+ * jw_sz_restrict_operator on the index lists of :250-371 jw_number_indices / jw_sz_indices), and
+ * builds a sector matrix term by term in get_number_preserving_sparse_operator (:1282-1597).
+ * Here a sector is an index space of `dim` basis states; position p holds basis state basis[p]
+ * (reference bit convention) in the reference's own enumeration order, and the kernels below act
+ * on vectors of `dim` complex128 amplitudes. */
+typedef struct ofb_sector ofb_sector;
+
+/* Two-table index map: for j = (hi, lo) split at lo_bits,
+ *   pos(j) = table_hi[hi * n_classes + popc(lo & class_mask)]
+ *          + table_lo[lo * n_classes + popc(hi-part of j & class_mask)]
+ * (n_classes == 1: the class index is 0).  j belongs to the sector iff for every constraint k
+ * popc(j & plus_mask[k]) - popc(j & minus_mask[k]) == value[k].  The basis list is enumerated on
+ * the device.  Replaces the itertools enumeration of sparse_tools.py:250-371. */
+int ofb_sector_create_tables(int n_qubits, int lo_bits, int n_classes, uint64_t class_mask,
+                             const uint64_t *table_hi, const uint32_t *table_lo, int n_constraints,
+                             const uint64_t *plus_mask, const uint64_t *minus_mask,
+                             const int32_t *value, int64_t dim, int device, ofb_sector **sector);
+/* Arbitrary basis list in the caller's order (custom spin maps, the excitation-ordered bases of
+ * sparse_tools.py:1370-1475 _iterate_basis_): lookups are a binary search (the reference uses
+ * numpy.searchsorted, :1573-1584). */
+int ofb_sector_create_list(int n_qubits, int64_t dim, const uint64_t *h_basis, int device,
+                           ofb_sector **sector);
+int ofb_sector_destroy(ofb_sector *sector);
+int ofb_sector_info(const ofb_sector *sector, int *n_qubits, int64_t *dim, int *mode);
+/* basis state at every position (jw_number_indices / jw_sz_indices as an array) */
+int ofb_sector_basis(ofb_sector *sector, uint64_t *h_basis /* dim */);
+/* Matrix-free (P H P)|psi> inside the sector: the action of
+ * jw_number_restrict_operator(get_sparse_operator(H)) / jw_sz_restrict_operator(...) on a vector
+ * without building either matrix.  ncols columns `ld` elements apart. */
+int ofb_sector_apply(ofb_plan *plan, ofb_sector *sector, const void *d_in, void *d_out, int ncols,
+                     int64_t ld, void *stream);
+int ofb_sector_apply_host(ofb_plan *plan, ofb_sector *sector, const void *h_in, void *h_out,
+                          int ncols);
+int ofb_sector_expectation(ofb_plan *plan, ofb_sector *sector, const void *d_state,
+                           double *h_out_ri /* 2 */, void *stream);
+/* diagonal of the restricted operator, float64[dim] (Davidson preconditioner) */
+int ofb_sector_diagonal(ofb_plan *plan, ofb_sector *sector, double *d_out, void *stream);
+/* jw_number_restrict_state / jw_sz_restrict_state (sparse_tools.py:426-476): sector[p] =
+ * full[basis[p]]; and the expansion of :507-509: full = 0, full[basis[p]] = sector[p]. */
+int ofb_sector_gather(ofb_sector *sector, const void *d_full, void *d_sector, void *stream);
+int ofb_sector_scatter(ofb_sector *sector, const void *d_sector, void *d_full, void *stream);
+/* CSC of the restricted operator (dim x dim), same contract as ofb_csc_count / ofb_csc_fill_host;
+ * accepts Pauli plans and projected (fermion-route) plans. */
+int ofb_sector_csc_count(ofb_plan *plan, ofb_sector *sector, int64_t *nnz, int *index_bits,
+                         void *stream);
+int ofb_sector_csc_fill_host(ofb_plan *plan, ofb_sector *sector, void *h_indptr, void *h_indices,
+                             void *h_data, int index_bits);
+
 #ifdef __cplusplus
 }
 #endif

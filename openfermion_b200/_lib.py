@@ -86,6 +86,20 @@ SIGNATURES = {
                                         c_void_p, c_void_p]),
     'ofb_vec_drop_imag': (c_int, [c_int64, c_void_p, c_void_p]),
     'ofb_vec_fill_random': (c_int, [c_int64, c_uint64, c_int, c_void_p, c_void_p]),
+    'ofb_sector_create_tables': (c_int, [c_int, c_int, c_int, c_uint64, c_void_p, c_void_p, c_int,
+                                         c_void_p, c_void_p, c_void_p, c_int64, c_int, P(c_void_p)]),
+    'ofb_sector_create_list': (c_int, [c_int, c_int64, c_void_p, c_int, P(c_void_p)]),
+    'ofb_sector_destroy': (c_int, [c_void_p]),
+    'ofb_sector_info': (c_int, [c_void_p, P(c_int), P(c_int64), P(c_int)]),
+    'ofb_sector_basis': (c_int, [c_void_p, c_void_p]),
+    'ofb_sector_apply': (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int64, c_void_p]),
+    'ofb_sector_apply_host': (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int]),
+    'ofb_sector_expectation': (c_int, [c_void_p, c_void_p, c_void_p, P(c_double), c_void_p]),
+    'ofb_sector_diagonal': (c_int, [c_void_p, c_void_p, c_void_p, c_void_p]),
+    'ofb_sector_gather': (c_int, [c_void_p, c_void_p, c_void_p, c_void_p]),
+    'ofb_sector_scatter': (c_int, [c_void_p, c_void_p, c_void_p, c_void_p]),
+    'ofb_sector_csc_count': (c_int, [c_void_p, c_void_p, P(c_int64), P(c_int), c_void_p]),
+    'ofb_sector_csc_fill_host': (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int]),
 }
 
 _NO_STATUS = {'ofb_version', 'ofb_last_error', 'ofb_launch_count'}

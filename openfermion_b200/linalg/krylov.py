@@ -115,6 +115,18 @@ class PlanOperator:
         self.plan.apply_device(d_in, d_out, 1, self.dim, stream)
 
 
+class SectorOperator:
+    """A compiled Pauli plan restricted to a symmetry sector (K7, csrc/sector.cu)."""
+
+    def __init__(self, plan, sector):
+        self.plan = plan
+        self.sector = sector
+        self.dim = sector.dim
+
+    def apply(self, d_in, d_out, stream=None):
+        self.sector.apply_device(self.plan, d_in, d_out, 1, self.dim, stream)
+
+
 class CsrOperator:
     """An already materialised scipy sparse matrix, uploaded once as CSR."""
 
@@ -152,9 +164,11 @@ class HostCallbackOperator:
 
 def as_device_operator(operator):
     from openfermion_b200.linalg.linear_qubit_operator import (
-        LinearQubitOperator, ParallelLinearQubitOperator)
-    if isinstance(operator, (PlanOperator, CsrOperator, HostCallbackOperator)):
+        LinearQubitOperator, ParallelLinearQubitOperator, SectorLinearQubitOperator)
+    if isinstance(operator, (PlanOperator, SectorOperator, CsrOperator, HostCallbackOperator)):
         return operator
+    if isinstance(operator, SectorLinearQubitOperator):
+        return SectorOperator(operator.plan, operator.sector)
     if isinstance(operator, LinearQubitOperator):
         return PlanOperator(operator.plan)
     if isinstance(operator, ParallelLinearQubitOperator):

@@ -9,6 +9,7 @@ import os
 import numpy
 import scipy.sparse.linalg
 
+from openfermion_b200 import sectors
 from openfermion_b200.compiler import compile_qubit_operator
 from openfermion_b200.ops import count_qubits
 from openfermion_b200.plan import PauliPlan
@@ -118,6 +119,77 @@ class ParallelLinearQubitOperator(scipy.sparse.linalg.LinearOperator):
         if not self.linear_operators:
             return numpy.zeros(numpy.asarray(X).shape)
         return self._fused._matmat(X)
+
+
+class SectorLinearQubitOperator(scipy.sparse.linalg.LinearOperator):
+    """Matrix-free action of a QubitOperator inside a Jordan-Wigner symmetry sector.
+
+    As a linear map it equals `jw_number_restrict_operator(get_sparse_operator(H), n_electrons)`
+    (sz_value None), `jw_sz_restrict_operator(get_sparse_operator(H), sz_value, n_electrons)`
+    otherwise (linalg/sparse_tools.py:375-423), with the same basis order, but neither
+    matrix is ever built: the vector has C(n, N) (or C(n/2, N_up) C(n/2, N_down)) amplitudes
+    and the sector kernel ranks / un-ranks basis states on the fly (csrc/sector.cu).
+    Not part of the reference API; it is what get_ground_state, expectation, Davidson and
+    jw_get_ground_state_at_particle_number use when handed a symbolic operator."""
+
+    def __init__(self, qubit_operator, n_qubits=None, n_electrons=None, sz_value=None,
+                 up_index=None, down_index=None):
+        if isinstance(qubit_operator, LinearQubitOperator):
+            base = qubit_operator
+            if n_qubits is not None and n_qubits != base.n_qubits:
+                raise ValueError('Invalid number of qubits specified.')
+        else:
+            base = LinearQubitOperator(qubit_operator, n_qubits)
+        if n_electrons is None and sz_value is None:
+            raise ValueError('Specify n_electrons, sz_value or both.')
+        self.linear_qubit_operator = base
+        self.qubit_operator = base.qubit_operator
+        self.n_qubits = base.n_qubits
+        self.n_electrons = n_electrons
+        self.sz_value = sz_value
+        self._spin_maps = (up_index, down_index)
+        self._sector = None
+        if sz_value is None:
+            dim = sectors.number_sector_tables(self.n_qubits, n_electrons, 0).dim
+        elif up_index is None and down_index is None:
+            tables = (sectors.sz_sector_tables(self.n_qubits, sz_value, 0) if n_electrons is None else
+                      sectors.sz_number_sector_tables(self.n_qubits, sz_value, n_electrons, 0))
+            dim = tables.dim
+        else:
+            dim = len(sectors.sz_indices_list(sz_value, self.n_qubits, n_electrons, up_index,
+                                              down_index))
+        super().__init__(shape=(dim, dim), dtype=complex)
+
+    @property
+    def plan(self):
+        return self.linear_qubit_operator.plan
+
+    @property
+    def sector(self):
+        """The device-resident index map (built on first access; raises without a GPU)."""
+        if self._sector is None:
+            if self.sz_value is None:
+                self._sector = sectors.Sector.number(self.n_qubits, self.n_electrons)
+            else:
+                self._sector = sectors.Sector.sz(self.n_qubits, self.sz_value, self.n_electrons,
+                                                 *self._spin_maps)
+        return self._sector
+
+    def indices(self):
+        """Basis state at every position: jw_number_indices / jw_sz_indices as an array."""
+        return self.sector.basis()
+
+    def diagonal(self):
+        return self.sector.diagonal_host(self.plan)
+
+    def _matvec(self, x):
+        arr = numpy.asarray(x)
+        vec = numpy.ascontiguousarray(arr.reshape(-1), dtype=numpy.complex128)
+        return self.sector.apply_host(self.plan, vec).reshape(arr.shape)
+
+    def _matmat(self, X):
+        X = numpy.asarray(X)
+        return self.sector.apply_host(self.plan, numpy.asfortranarray(X, dtype=numpy.complex128))
 
 
 def apply_operator(args):

@@ -12,10 +12,11 @@ import numpy
 import scipy.sparse
 import scipy.sparse.linalg
 
-from openfermion_b200 import ops
+from openfermion_b200 import ops, sectors
 from openfermion_b200.compiler import compile_fermion_terms, compile_qubit_operator
 from openfermion_b200.linalg import krylov
-from openfermion_b200.linalg.linear_qubit_operator import LinearQubitOperator
+from openfermion_b200.linalg.linear_qubit_operator import (LinearQubitOperator,
+                                                           SectorLinearQubitOperator)
 from openfermion_b200.ops import count_qubits
 from openfermion_b200.plan import PauliPlan
 
@@ -157,6 +158,10 @@ def expectation(operator, state):
             if state.size != operator.shape[1]:
                 raise ValueError('Dimension mismatch')
             return operator.plan.expectation_host(state)
+        if isinstance(operator, SectorLinearQubitOperator):
+            if state.size != operator.shape[1]:
+                raise ValueError('Dimension mismatch')
+            return operator.sector.expectation_host(operator.plan, state)
         applied = krylov.apply_any(operator, state)
         if len(state.shape) == 1:
             return numpy.dot(numpy.conjugate(state), applied)
@@ -192,52 +197,65 @@ def inner_product(state_1, state_2):
 
 
 # ----------------------------------------------------------------------------
-# Jordan-Wigner symmetry-sector helpers
-# (sparse_tools.py:273-345, 375-423, 477-513).  Index selection is host arithmetic as in
-# the reference; the eigen-solve inside the sector runs on the device (CSR SpMV + Lanczos).
+# Jordan-Wigner symmetry sectors
+# (sparse_tools.py:273-513 and :1282-1597).  The reference materialises the 2^n x 2^n matrix
+# and slices it; that route is kept for already materialised inputs.  Symbolic operators
+# (QubitOperator / FermionOperator / LinearQubitOperator) never leave the sector: the index
+# map lives on the device (openfermion_b200/sectors.py, csrc/sector.cu) and the restricted
+# operator is either applied matrix-free or assembled directly as a dim x dim CSC.
 # ----------------------------------------------------------------------------
 def jw_number_indices(n_electrons, n_qubits):
     """Indices of all basis states with n_electrons occupied modes, in the reference's order
     (itertools.combinations over bit positions, sparse_tools.py:273-292)."""
-    occupations = itertools.combinations(range(n_qubits), n_electrons)
-    return [sum(1 << n for n in occupation) for occupation in occupations]
+    return sectors.number_indices_list(n_electrons, n_qubits)
 
 
 def jw_sz_indices(sz_value, n_qubits, n_electrons=None, up_index=None, down_index=None):
     """Indices of basis states with fixed S_z (sparse_tools.py:295-372); up = 2i, down = 2i+1
     by default (utils/indexing.py:17,29)."""
-    up_index = up_index or (lambda i: 2 * i)
-    down_index = down_index or (lambda i: 2 * i + 1)
-    if n_qubits % 2 != 0:
-        raise ValueError('Number of qubits must be even')
-    if not (2.0 * sz_value).is_integer():
-        raise ValueError('Sz value must be an integer or half-integer')
-    n_sites = n_qubits // 2
-    sz_integer = int(2.0 * sz_value)
-    indices = []
+    return sectors.sz_indices_list(sz_value, n_qubits, n_electrons, up_index, down_index)
 
-    def pair(outer_map, n_outer, inner_map, n_inner):
-        # every arrangement of the outer spin species with every arrangement of the inner one
-        inner = list(itertools.combinations(range(n_sites), n_inner))
-        for outer_occ in itertools.combinations(range(n_sites), n_outer):
-            outer_modes = [outer_map(i) for i in outer_occ]
-            for inner_occ in inner:
-                occupation = outer_modes + [inner_map(i) for i in inner_occ]
-                indices.append(sum(1 << (n_qubits - 1 - m) for m in occupation))
 
-    if n_electrons is not None:
-        if (n_electrons + sz_integer) % 2 != 0 or n_electrons < abs(sz_integer):
-            raise ValueError('The specified particle number and sz value are incompatible.')
-        num_up = (n_electrons + sz_integer) // 2
-        pair(up_index, num_up, down_index, n_electrons - num_up)
-    else:
-        more_map, less_map = (down_index, up_index) if sz_integer < 0 else (up_index, down_index)
-        for n in range(abs(sz_integer), n_sites + 1):
-            pair(more_map, n, less_map, n - abs(sz_integer))
-    return indices
+def _is_symbolic(operator):
+    return (ops.is_qubit_operator(operator) or ops.is_fermion_operator(operator)
+            or isinstance(operator, LinearQubitOperator))
+
+
+def _sector_plan(operator, n_qubits):
+    """Compiled plan of a symbolic operator for the sector kernels: (plan, owned)."""
+    if isinstance(operator, LinearQubitOperator):
+        if n_qubits is not None and n_qubits != operator.n_qubits:
+            raise ValueError('Invalid number of qubits specified.')
+        return operator.plan, False
+    needed = count_qubits(operator)
+    if n_qubits is None:
+        n_qubits = needed
+    if n_qubits < needed:
+        raise ValueError('Invalid number of qubits specified.')
+    if ops.is_fermion_operator(operator):
+        return PauliPlan.projected_rows(n_qubits, *compile_fermion_terms(operator.terms, n_qubits)), True
+    x, z, c = compile_qubit_operator(operator, n_qubits)
+    return PauliPlan(n_qubits, x, z, c), True
+
+
+def _restricted_csc(operator, n_qubits, make_sector):
+    plan, owned = _sector_plan(operator, n_qubits)
+    sector = make_sector(plan.n_qubits)
+    try:
+        return sector.csc_host(plan)
+    finally:
+        sector.close()
+        if owned:
+            plan.close()
 
 
 def jw_number_restrict_operator(operator, n_electrons, n_qubits=None):
+    """Operator restricted to n_electrons particles (sparse_tools.py:375-392).  Matrices are
+    sliced like the reference does; symbolic operators are assembled inside the sector on the
+    device (the full matrix is never built)."""
+    if _is_symbolic(operator):
+        return _restricted_csc(operator, n_qubits,
+                               lambda n: sectors.Sector.number(n, n_electrons))
     if n_qubits is None:
         n_qubits = int(numpy.log2(operator.shape[0]))
     select = jw_number_indices(n_electrons, n_qubits)
@@ -246,6 +264,12 @@ def jw_number_restrict_operator(operator, n_electrons, n_qubits=None):
 
 def jw_sz_restrict_operator(operator, sz_value, n_electrons=None, n_qubits=None, up_index=None,
                             down_index=None):
+    """Operator restricted to a given S_z (and optionally particle number)
+    (sparse_tools.py:395-423)."""
+    if _is_symbolic(operator):
+        return _restricted_csc(operator, n_qubits,
+                               lambda n: sectors.Sector.sz(n, sz_value, n_electrons, up_index,
+                                                           down_index))
     if n_qubits is None:
         n_qubits = int(numpy.log2(operator.shape[0]))
     select = jw_sz_indices(sz_value, n_qubits, n_electrons=n_electrons, up_index=up_index,
@@ -253,9 +277,46 @@ def jw_sz_restrict_operator(operator, sz_value, n_electrons=None, n_qubits=None,
     return operator[numpy.ix_(select, select)]
 
 
-def jw_get_ground_state_at_particle_number(sparse_operator, particle_number):
+def jw_number_restrict_state(state, n_electrons, n_qubits=None):
+    """state[jw_number_indices] (sparse_tools.py:426-442)."""
+    if n_qubits is None:
+        n_qubits = int(numpy.log2(state.shape[0]))
+    return state[jw_number_indices(n_electrons, n_qubits)]
+
+
+def jw_sz_restrict_state(state, sz_value, n_electrons=None, n_qubits=None, up_index=None,
+                         down_index=None):
+    """state[jw_sz_indices] (sparse_tools.py:445-476)."""
+    if n_qubits is None:
+        n_qubits = int(numpy.log2(state.shape[0]))
+    return state[jw_sz_indices(sz_value, n_qubits, n_electrons=n_electrons, up_index=up_index,
+                               down_index=down_index)]
+
+
+def jw_get_ground_state_at_particle_number(sparse_operator, particle_number, sz_value=None,
+                                           expand=True):
     """Lowest eigenpair inside a particle-number sector, expanded back to 2^n amplitudes
-    (sparse_tools.py:477-513)."""
+    (sparse_tools.py:477-513).
+
+    Beyond the reference: a symbolic operator or LinearQubitOperator is solved matrix-free
+    inside the sector (device Lanczos on the sector kernel); `sz_value` narrows the sector
+    to fixed S_z as well, and expand=False returns the dim-long sector vector (the 2^n
+    expansion of a 32-qubit state is 64 GiB)."""
+    if _is_symbolic(sparse_operator):
+        from openfermion_b200.linalg.linear_qubit_operator import SectorLinearQubitOperator
+        restricted = SectorLinearQubitOperator(sparse_operator, n_electrons=particle_number,
+                                               sz_value=sz_value)
+        if restricted.shape[0] - 1 <= 1:
+            dense = restricted.matmat(numpy.eye(restricted.shape[0], dtype=complex))
+            eigvals, eigvecs = numpy.linalg.eigh(dense)
+            energy, state = eigvals[0], eigvecs[:, 0]
+        else:
+            energy, state = get_ground_state(restricted)
+        if not expand:
+            return energy, state
+        return energy, restricted.sector.expand_state_host(state)
+    if sz_value is not None:
+        raise ValueError('sz_value needs a symbolic operator or a LinearQubitOperator.')
     n_qubits = int(numpy.log2(sparse_operator.shape[0]))
     restricted = jw_number_restrict_operator(sparse_operator, particle_number, n_qubits)
     if restricted.shape[0] - 1 <= 1:
@@ -263,6 +324,85 @@ def jw_get_ground_state_at_particle_number(sparse_operator, particle_number):
         energy, state = eigvals[0], eigvecs[:, 0]
     else:
         energy, state = get_ground_state(scipy.sparse.csc_matrix(restricted))
+    if not expand:
+        return energy, state
     expanded = numpy.zeros(2**n_qubits, dtype=complex)
     expanded[jw_number_indices(particle_number, n_qubits)] = state
     return energy, expanded
+
+
+def _excited_determinants(reference, occupied, unoccupied, order, n_qubits):
+    for occ in itertools.combinations(occupied, order):
+        cleared = reference
+        for mode in occ:
+            cleared ^= 1 << (n_qubits - 1 - mode)
+        for unocc in itertools.combinations(unoccupied, order):
+            state = cleared
+            for mode in unocc:
+                state ^= 1 << (n_qubits - 1 - mode)
+            yield state
+
+
+def _number_preserving_basis(reference_determinant, excitation_level, spin_preserving):
+    """Integer encodings (mode i = bit n-1-i) of the determinants in the order of
+    _iterate_basis_ (sparse_tools.py:1370-1475): by excitation rank from the reference and,
+    with spin_preserving, by (alpha rank, beta rank) inside each rank."""
+    reference_determinant = [bool(b) for b in reference_determinant]
+    n = len(reference_determinant)
+    ref_int = sum(1 << (n - 1 - i) for i, b in enumerate(reference_determinant) if b)
+    basis = []
+    if not spin_preserving:
+        occupied = [i for i, b in enumerate(reference_determinant) if b]
+        unoccupied = [i for i, b in enumerate(reference_determinant) if not b]
+        for order in range(excitation_level + 1):
+            basis.extend(_excited_determinants(ref_int, occupied, unoccupied, order, n))
+        return basis
+    occ_a = [i for i in range(0, n, 2) if reference_determinant[i]]
+    unocc_a = [i for i in range(0, n, 2) if not reference_determinant[i]]
+    occ_b = [i for i in range(1, n, 2) if reference_determinant[i]]
+    unocc_b = [i for i in range(1, n, 2) if not reference_determinant[i]]
+    alpha_level = min(len(occ_a), excitation_level)
+    beta_level = min(len(occ_b), excitation_level)
+    for order in range(excitation_level + 1):
+        for alpha_order in range(alpha_level + 1):
+            beta_order = order - alpha_order
+            if beta_order < 0 or beta_order > beta_level:
+                continue
+            # the alpha excitation is the outer loop, the beta excitation the inner one
+            beta_flips = [s ^ ref_int for s in
+                          _excited_determinants(ref_int, occ_b, unocc_b, beta_order, n)]
+            for alpha_state in _excited_determinants(ref_int, occ_a, unocc_a, alpha_order, n):
+                basis.extend(alpha_state ^ flip for flip in beta_flips)
+    return basis
+
+
+def get_number_preserving_sparse_operator(fermion_op, num_qubits, num_electrons,
+                                          spin_preserving=False, reference_determinant=None,
+                                          excitation_level=None):
+    """CSC of a FermionOperator inside a particle-number (and optionally S_z, optionally
+    excitation-truncated) sector, basis ordered by excitation rank from the reference
+    determinant (sparse_tools.py:1282-1369).  The reference loops over terms and basis states
+    in Python (:1478-1597); here the normal-ordered terms become projected scatter rows and
+    the sector CSC kernels place them through a device-side search of the basis."""
+    if reference_determinant is None:
+        reference_determinant = [i < num_electrons for i in range(num_qubits)]
+    reference_determinant = list(numpy.asarray(reference_determinant).astype(bool))
+    if excitation_level is None:
+        excitation_level = num_electrons
+    basis = _number_preserving_basis(reference_determinant, excitation_level, spin_preserving)
+    converted = ops.FermionOperator()
+    converted.terms = dict(fermion_op.terms)
+    ordered = ops.normal_ordered(converted)
+    is_complex = False
+    for term, coefficient in ordered.terms.items():
+        if sum(1 if kind else -1 for _, kind in term) != 0:
+            raise ValueError("The supplied operator doesn't preserve particle number")
+        if isinstance(coefficient, (complex, numpy.complexfloating)):
+            is_complex = True
+    plan = PauliPlan.projected_rows(num_qubits, *compile_fermion_terms(ordered.terms, num_qubits))
+    sector = sectors.Sector.from_list(num_qubits, basis)
+    try:
+        return sector.csc_host(plan, dtype=numpy.complex128 if is_complex else numpy.float64)
+    finally:
+        sector.close()
+        plan.close()

@@ -6,8 +6,9 @@ reference): a dict {((index, action), ...): coefficient}.  Upstream `QubitOperat
 machines where upstream is not installed (the GPU box) and implement only what the
 linalg functions, tests and benches need: construction from the reference's string /
 tuple syntax, +, -, scalar *, Pauli products, compress() and get_operator_groups().
-The symbolic algebra of the reference (sympy coefficients, normal ordering, ...) is out
-of scope.
+The symbolic algebra of the reference (sympy coefficients, ...) is out of scope
+(SURVEY.md section 2, rows 5 and 7); fermionic normal ordering is restated below because
+get_number_preserving_sparse_operator sums its terms in normal-ordered term order.
 """
 import re
 
@@ -208,6 +209,42 @@ class FermionOperator(_TermDict):
         for k in out.terms:
             out.terms[k] = out.terms[k] * other
         return out
+
+
+def _normal_ordered_ladder_term(term, coefficient):
+    """Normal-ordered form of one fermionic ladder product: raising operators first, modes
+    descending (transforms/opconversions/term_reordering.py:153-233 with parity = -1)."""
+    term = list(term)
+    ordered = FermionOperator()
+    for i in range(1, len(term)):
+        for j in range(i, 0, -1):
+            right, left = term[j], term[j - 1]
+            if right[1] and not left[1]:
+                # a a^ = delta - a^ a
+                term[j - 1], term[j] = right, left
+                coefficient = coefficient * -1
+                if right[0] == left[0]:
+                    ordered += _normal_ordered_ladder_term(tuple(term[:j - 1] + term[j + 1:]),
+                                                           -1 * coefficient)
+            elif right[1] == left[1]:
+                if right[0] == left[0]:
+                    return ordered  # a a = a^ a^ = 0
+                if right[0] > left[0]:
+                    term[j - 1], term[j] = right, left
+                    coefficient = coefficient * -1
+    ordered += FermionOperator(tuple(term), coefficient)
+    return ordered
+
+
+def normal_ordered(operator):
+    """normal_ordered for FermionOperators (term_reordering.py:62-150, fermionic branch):
+    terms are processed in dict order and accumulated with +=."""
+    if not is_fermion_operator(operator):
+        raise TypeError('Can only normal order FermionOperator here.')
+    ordered = FermionOperator()
+    for term, coefficient in operator.terms.items():
+        ordered += _normal_ordered_ladder_term(term, coefficient)
+    return ordered
 
 
 def _class_names(obj):

@@ -13,6 +13,7 @@ import sys
 import zlib
 
 import numpy
+import scipy.sparse
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(HERE)
@@ -184,8 +185,156 @@ def lih_case():
     print('lih: nnz', csc.nnz, 'E0', e0, 'T', len(strs))
 
 
+def sector_cases():
+    """Symmetry-sector functions: index lists, restricted
+    operators, get_number_preserving_sparse_operator and sector ground states of the real
+    reference; the oracle restatement (oracle/sector_oracle.py) and the repo's own
+    normal_ordered are asserted against the reference on the way."""
+    import sector_oracle as so
+    from openfermion.linalg import sparse_tools as rst
+    from openfermion.transforms.opconversions.term_reordering import normal_ordered
+    from openfermion_b200 import ops as our_ops
+    cases = {}
+    # 1. index lists
+    lists = []
+    for n, ne in ((1, 0), (1, 1), (5, 2), (6, 3), (7, 0), (7, 7), (9, 4)):
+        ref = rst.jw_number_indices(ne, n)
+        assert ref == so.jw_number_indices(ne, n)
+        key = 'number_{}_{}'.format(n, ne)
+        cases['lists/' + key] = numpy.array(ref, dtype=numpy.int64)
+        lists.append(key)
+    for n, sz, ne in ((2, 0.5, None), (4, 0.0, None), (6, 0.5, None), (6, -1.0, None), (8, 0.0, 4),
+                      (6, 0.5, 3), (6, -1.5, 3), (8, 1.0, 4), (10, -0.5, 5), (8, 2.0, None)):
+        ref = rst.jw_sz_indices(sz, n, ne)
+        assert ref == so.jw_sz_indices(sz, n, ne)
+        key = 'sz_{}_{}_{}'.format(n, sz, ne)
+        cases['lists/' + key] = numpy.array(ref, dtype=numpy.int64)
+        lists.append(key)
+    # custom spin maps (first half up, second half down)
+    ref = rst.jw_sz_indices(0.0, 6, 2, up_index=lambda i: i, down_index=lambda i: i + 3)
+    assert ref == so.jw_sz_indices(0.0, 6, 2, up_index=lambda i: i, down_index=lambda i: i + 3)
+    cases['lists/sz_blocked_6_0.0_2'] = numpy.array(ref, dtype=numpy.int64)
+    cases['list_names'] = numpy.array(lists, dtype=str)
+
+    # 2. restricted operators + 5. sector matvec + 4. ground states
+    rng = numpy.random.default_rng(20261020)
+    fops = {
+        'hubbard_2x2': (fermi_hubbard(2, 2, 1.0, 4.0), 8),
+        'hubbard_2x2_mu_h': (fermi_hubbard(2, 2, 1.0, 4.0, 0.3, 0.2), 8),
+        'molecular_6': (get_fermion_operator(random_interaction_operator(3, expand_spin=True, real=True, seed=5)), 6),
+        'molecular_8': (get_fermion_operator(random_interaction_operator(4, expand_spin=True, real=True, seed=11)), 8),
+        'molecular_4_complex': (get_fermion_operator(random_interaction_operator(4, expand_spin=False, real=False, seed=9)), 4),
+    }
+    sector_list = {
+        'hubbard_2x2': [('number', 4, None), ('number', 3, None), ('sz', 4, 0.0), ('sz', None, 0.0), ('sz', 3, 0.5)],
+        'hubbard_2x2_mu_h': [('number', 5, None), ('sz', None, -1.0)],
+        'molecular_6': [('number', 3, None), ('sz', 3, 0.5), ('sz', None, -0.5), ('sz', 2, 0.0)],
+        'molecular_8': [('number', 4, None), ('sz', 4, 0.0), ('sz', None, 1.0)],
+        'molecular_4_complex': [('number', 2, None), ('sz', 2, 0.0)],
+    }
+    names = []
+    for name, (fop, n) in fops.items():
+        qop = jordan_wigner(fop)
+        fs, fc, fic = pack_terms(fop.terms, fermion_term_str)
+        qs, qc, qic = pack_terms(qop.terms, qubit_term_str)
+        cases[name + '/n_qubits'] = numpy.array(n)
+        cases[name + '/fermion_terms'] = fs
+        cases[name + '/fermion_coeffs'] = fc
+        cases[name + '/fermion_coeff_is_complex'] = fic
+        cases[name + '/qubit_terms'] = qs
+        cases[name + '/qubit_coeffs'] = qc
+        cases[name + '/qubit_coeff_is_complex'] = qic
+        full_f = get_sparse_operator(fop, n)
+        full_q = get_sparse_operator(qop, n)
+        tags = []
+        for kind, ne, sz in sector_list[name]:
+            tag = '{}_{}_{}'.format(kind, ne, sz)
+            if kind == 'number':
+                res_f = rst.jw_number_restrict_operator(full_f, ne, n)
+                res_q = rst.jw_number_restrict_operator(full_q, ne, n)
+                idx = so.jw_number_indices(ne, n)
+            else:
+                res_f = rst.jw_sz_restrict_operator(full_f, sz, ne, n)
+                res_q = rst.jw_sz_restrict_operator(full_q, sz, ne, n)
+                idx = so.jw_sz_indices(sz, n, ne)
+            assert same_csc(scipy.sparse.csc_matrix(res_f), scipy.sparse.csc_matrix(so.restrict_operator(full_f, idx)))
+            for route, res in (('f', res_f), ('q', res_q)):
+                res = scipy.sparse.csc_matrix(res)
+                res.sort_indices()
+                cases['{}/{}/{}_indptr'.format(name, tag, route)] = res.indptr
+                cases['{}/{}/{}_indices'.format(name, tag, route)] = res.indices
+                cases['{}/{}/{}_data'.format(name, tag, route)] = res.data
+            dim = res_f.shape[0]
+            v = rng.normal(size=dim) + 1j * rng.normal(size=dim)
+            cases['{}/{}/v'.format(name, tag)] = v
+            cases['{}/{}/Hv'.format(name, tag)] = res_f @ v
+            cases['{}/{}/expectation'.format(name, tag)] = numpy.array(expectation(scipy.sparse.csc_matrix(res_f), v))
+            cases['{}/{}/diagonal'.format(name, tag)] = res_f.diagonal()
+            if dim > 2:
+                cases['{}/{}/e0'.format(name, tag)] = numpy.array(
+                    numpy.linalg.eigvalsh(res_f.toarray())[0])
+            tags.append(tag)
+        cases[name + '/sectors'] = numpy.array(tags, dtype=str)
+        names.append(name)
+    # jw_get_ground_state_at_particle_number (sparse_tools_test.py style known answers)
+    for name, ne in (('hubbard_2x2', 2), ('hubbard_2x2', 4), ('molecular_6', 3), ('molecular_6', 0)):
+        fop, n = fops[name]
+        e, state = rst.jw_get_ground_state_at_particle_number(get_sparse_operator(fop, n), ne)
+        e2, _ = so.ground_state_at_particle_number(get_sparse_operator(fop, n), ne)
+        assert abs(e - e2) < 1e-10
+        cases['{}/gs_number_{}/energy'.format(name, ne)] = numpy.array(e)
+        cases['{}/gs_number_{}/support'.format(name, ne)] = numpy.nonzero(numpy.abs(state) > 1e-12)[0]
+    cases['names'] = numpy.array(names, dtype=str)
+
+    # 3. get_number_preserving_sparse_operator
+    np_cases = []
+    specs = [
+        ('hubbard_2x2', 4, False, None, None),
+        ('hubbard_2x2', 4, True, None, None),
+        ('hubbard_2x2', 3, True, [True, False, True, True, False, False, False, False], None),
+        ('molecular_6', 3, False, None, 2),
+        ('molecular_6', 2, True, [False, True, True, False, False, False], 1),
+        ('molecular_8', 4, True, None, 2),
+        ('molecular_8', 4, False, [True, True, False, False, True, True, False, False], None),
+        ('molecular_4_complex', 2, False, None, None),
+    ]
+    for k, (name, ne, spin, refdet, level) in enumerate(specs):
+        fop, n = fops[name]
+        ref = rst.get_number_preserving_sparse_operator(fop, n, ne, spin_preserving=spin,
+                                                         reference_determinant=refdet,
+                                                         excitation_level=level)
+        # the repo's normal ordering must be bit-identical to the reference's (term order too)
+        ordered_ref = normal_ordered(fop)
+        mine = our_ops.FermionOperator()
+        mine.terms = dict(fop.terms)
+        ordered_mine = our_ops.normal_ordered(mine)
+        assert list(ordered_ref.terms.items()) == list(ordered_mine.terms.items()), name
+        again = so.get_number_preserving_sparse_operator(ordered_ref.terms, n, ne, spin, refdet, level)
+        assert same_csc(ref, again), (name, k)
+        key = 'np{}'.format(k)
+        cases[key + '/operator'] = numpy.array(name)
+        cases[key + '/num_electrons'] = numpy.array(ne)
+        cases[key + '/spin_preserving'] = numpy.array(spin)
+        cases[key + '/reference_determinant'] = numpy.array(refdet if refdet is not None else [], dtype=bool)
+        cases[key + '/excitation_level'] = numpy.array(-1 if level is None else level)
+        cases[key + '/indptr'] = ref.indptr
+        cases[key + '/indices'] = ref.indices
+        cases[key + '/data'] = ref.data
+        cases[key + '/dtype'] = numpy.array(str(ref.dtype))
+        np_cases.append(key)
+    cases['np_names'] = numpy.array(np_cases, dtype=str)
+    numpy.savez_compressed(os.path.join(GOLDEN, 'sector_cases.npz'), **cases)
+    print('sector_cases:', len(lists), 'lists,', len(names), 'operators,', len(np_cases), 'number-preserving cases')
+
+
 if __name__ == '__main__':
     os.makedirs(GOLDEN, exist_ok=True)
-    qubit_cases()
-    fermion_cases()
-    lih_case()
+    which = sys.argv[1:] or ['qubit', 'fermion', 'lih', 'sector']
+    if 'qubit' in which:
+        qubit_cases()
+    if 'fermion' in which:
+        fermion_cases()
+    if 'lih' in which:
+        lih_case()
+    if 'sector' in which:
+        sector_cases()

@@ -22,12 +22,15 @@ def qubit_operator_from(strs, coeffs, is_complex=None):
     return op
 
 
-def fermion_operator_from(strs, coeffs):
+def fermion_operator_from(strs, coeffs, is_complex=None):
     op = FermionOperator()
-    for s, c in zip(strs, coeffs):
+    for k, (s, c) in enumerate(zip(strs, coeffs)):
         key = tuple((int(tok.rstrip('^')), 1 if tok.endswith('^') else 0) for tok in str(s).split())
         c = complex(c)
-        op.terms[key] = c.real if c.imag == 0 else c
+        if is_complex is None:
+            op.terms[key] = c.real if c.imag == 0 else c
+        else:  # keep the reference's coefficient type (it decides the dtype of some outputs)
+            op.terms[key] = c if is_complex[k] else c.real
     return op
 
 

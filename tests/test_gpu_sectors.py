@@ -1,0 +1,207 @@
+"""GPU: parity of the symmetry-sector kernels (csrc/sector.cu, through the Python mirror and
+the C ABI) against the golden vectors of the real reference (tests/golden/sector_cases.npz),
+the sector oracle, and -- at sizes the reference cannot reach -- size-independent
+properties (Hermiticity, agreement with the full-space kernel, known Hubbard energies).
+Bars: indices bit-exact, values / matvecs / expectations within 1e-12 relative, energies
+within 1e-10."""
+import numpy
+import pytest
+import scipy.sparse
+
+import helpers
+import pauli_oracle
+import sector_oracle
+from helpers import fermion_operator_from, golden, qubit_operator_from
+from openfermion_b200 import models, sectors
+from openfermion_b200.linalg import (LinearQubitOperator, SectorLinearQubitOperator, expectation,
+                                     get_ground_state, get_number_preserving_sparse_operator,
+                                     jw_get_ground_state_at_particle_number,
+                                     jw_number_restrict_operator, jw_sz_restrict_operator)
+
+pytestmark = pytest.mark.gpu
+RTOL = 1e-12
+DATA = golden('sector_cases.npz')
+LIST_NAMES = [str(n) for n in DATA['list_names']]
+OPERATORS = [str(n) for n in DATA['names']]
+NP_CASES = [str(n) for n in DATA['np_names']]
+
+
+def _parse_tag(tag):
+    kind, ne, sz = str(tag).split('_')
+    return kind, (None if ne == 'None' else int(ne)), (None if sz == 'None' else float(sz))
+
+
+def _operators(name):
+    n = int(DATA[name + '/n_qubits'])
+    fop = fermion_operator_from(DATA[name + '/fermion_terms'], DATA[name + '/fermion_coeffs'],
+                                DATA[name + '/fermion_coeff_is_complex'])
+    qop = qubit_operator_from(DATA[name + '/qubit_terms'], DATA[name + '/qubit_coeffs'],
+                              DATA[name + '/qubit_coeff_is_complex'])
+    return n, fop, qop
+
+
+def _cases():
+    return [(name, str(tag)) for name in OPERATORS for tag in DATA[name + '/sectors']]
+
+
+@pytest.mark.parametrize('name', LIST_NAMES)
+def test_device_basis_enumeration_equals_reference_lists(name):
+    parts = name.split('_')
+    want = DATA['lists/' + name].astype(numpy.uint64)
+    if parts[0] == 'number':
+        sector = sectors.Sector.number(int(parts[1]), int(parts[2]))
+    else:
+        ne = None if parts[3] == 'None' else int(parts[3])
+        sector = sectors.Sector.sz(int(parts[1]), float(parts[2]), ne)
+    assert sector.dim == len(want)
+    assert numpy.array_equal(sector.basis(), want)
+
+
+def test_custom_spin_map_sector_uses_search_mode():
+    want = DATA['lists/sz_blocked_6_0.0_2'].astype(numpy.uint64)
+    sector = sectors.Sector.sz(6, 0.0, 2, up_index=lambda i: i, down_index=lambda i: i + 3)
+    assert sector.mode == 1 and numpy.array_equal(sector.basis(), want)
+    hub = models.random_pauli_sum(6, 30, 3, True)
+    full = pauli_oracle.qubit_operator_sparse(hub.terms, 6)
+    idx = want.astype(numpy.int64)
+    rng = numpy.random.default_rng(1)
+    v = rng.normal(size=len(idx)) + 1j * rng.normal(size=len(idx))
+    got = sector.apply_host(LinearQubitOperator(hub, 6).plan, v)
+    assert helpers.close(got, full[numpy.ix_(idx, idx)] @ v, RTOL)
+
+
+@pytest.mark.parametrize('name,tag', _cases())
+def test_sector_matvec_expectation_diagonal(name, tag):
+    n, _, qop = _operators(name)
+    kind, ne, sz = _parse_tag(tag)
+    op = SectorLinearQubitOperator(qop, n, n_electrons=ne, sz_value=sz)
+    v = DATA['{}/{}/v'.format(name, tag)]
+    want = DATA['{}/{}/Hv'.format(name, tag)]
+    assert op.shape == (len(v), len(v))
+    got = op * v
+    assert got.dtype == numpy.complex128
+    assert helpers.close(got, want, RTOL)
+    # matmat, two columns
+    both = op.matmat(numpy.stack([v, 1j * v], axis=1))
+    assert helpers.close(both[:, 0], want, RTOL) and helpers.close(both[:, 1], 1j * want, RTOL)
+    e_want = complex(DATA['{}/{}/expectation'.format(name, tag)])
+    assert abs(expectation(op, v) - e_want) <= RTOL * max(abs(e_want), 1.0)
+    diag = DATA['{}/{}/diagonal'.format(name, tag)]
+    assert helpers.close(op.diagonal(), diag.real, RTOL)
+
+
+@pytest.mark.parametrize('name,tag', _cases())
+def test_restricted_csc_from_symbolic_operators(name, tag):
+    n, fop, qop = _operators(name)
+    kind, ne, sz = _parse_tag(tag)
+    if kind == 'number':
+        got_f = jw_number_restrict_operator(fop, ne, n)
+        got_q = jw_number_restrict_operator(qop, ne, n)
+    else:
+        got_f = jw_sz_restrict_operator(fop, sz, ne, n)
+        got_q = jw_sz_restrict_operator(LinearQubitOperator(qop, n), sz, ne)
+    key = '{}/{}/'.format(name, tag)
+    # fermion route: structure bit-exact, values to 1e-12
+    helpers.assert_csc_matches(got_f, DATA[key + 'f_indptr'], DATA[key + 'f_indices'], DATA[key + 'f_data'])
+    # Pauli route: the reference's own full matrix carries cancellation residues
+    coeff_abs_sum = float(numpy.sum(numpy.abs(DATA[name + '/qubit_coeffs'])))
+    helpers.assert_csc_matches_modulo_residues(got_q, DATA[key + 'q_indptr'], DATA[key + 'q_indices'],
+                                               DATA[key + 'q_data'], coeff_abs_sum)
+
+
+def test_restrict_functions_still_slice_materialised_matrices():
+    n, fop, _ = _operators('hubbard_2x2')
+    full = pauli_oracle.jordan_wigner_sparse(fop.terms, n)
+    got = scipy.sparse.csc_matrix(jw_number_restrict_operator(full, 4))
+    key = 'hubbard_2x2/number_4_None/'
+    got.sort_indices()
+    assert numpy.array_equal(got.indices, DATA[key + 'f_indices'])
+    assert numpy.array_equal(got.data, DATA[key + 'f_data'])
+    dense = jw_sz_restrict_operator(full.toarray(), 0.0, 4)
+    assert dense.shape == (36, 36)
+
+
+@pytest.mark.parametrize('key', NP_CASES)
+def test_get_number_preserving_sparse_operator(key):
+    refdet = DATA[key + '/reference_determinant']
+    level = int(DATA[key + '/excitation_level'])
+    name = str(DATA[key + '/operator'])
+    n, fop, _ = _operators(name)
+    got = get_number_preserving_sparse_operator(
+        fop, n, int(DATA[key + '/num_electrons']), spin_preserving=bool(DATA[key + '/spin_preserving']),
+        reference_determinant=None if refdet.size == 0 else list(refdet),
+        excitation_level=None if level < 0 else level)
+    assert scipy.sparse.isspmatrix_csc(got)
+    assert str(got.dtype) == str(DATA[key + '/dtype'])
+    helpers.assert_csc_matches(got, DATA[key + '/indptr'], DATA[key + '/indices'], DATA[key + '/data'])
+
+
+def test_number_preserving_operator_rejects_non_conserving_terms():
+    from openfermion_b200.ops import FermionOperator
+    with pytest.raises(ValueError, match="doesn't preserve particle number"):
+        get_number_preserving_sparse_operator(FermionOperator('2^ 1^ 0'), 4, 2)
+
+
+@pytest.mark.parametrize('name,ne', [('hubbard_2x2', 2), ('hubbard_2x2', 4), ('molecular_6', 3),
+                                     ('molecular_6', 0)])
+def test_ground_state_at_particle_number(name, ne):
+    n, fop, qop = _operators(name)
+    want = float(DATA['{}/gs_number_{}/energy'.format(name, ne)])
+    support = set(sector_oracle.jw_number_indices(ne, n))
+    # symbolic operator: matrix-free inside the sector
+    e, state = jw_get_ground_state_at_particle_number(qop, ne)
+    assert abs(e - want) < 1e-10
+    assert state.shape == (2**n,) and set(numpy.nonzero(numpy.abs(state) > 1e-9)[0]) <= support
+    # materialised matrix: the reference's own call
+    full = pauli_oracle.jordan_wigner_sparse(fop.terms, n)
+    e2, state2 = jw_get_ground_state_at_particle_number(full, ne)
+    assert abs(e2 - want) < 1e-10
+    assert abs(numpy.vdot(state2, full @ state2) - want) < 1e-9
+
+
+@pytest.mark.parametrize('name,tag', [c for c in _cases() if c[0] != 'molecular_4_complex'])
+def test_sector_ground_energy_by_device_lanczos(name, tag):
+    key = '{}/{}/e0'.format(name, tag)
+    if key not in DATA.files:
+        pytest.skip('sector too small')
+    n, _, qop = _operators(name)
+    kind, ne, sz = _parse_tag(tag)
+    op = SectorLinearQubitOperator(qop, n, n_electrons=ne, sz_value=sz)
+    e, vec = get_ground_state(op)
+    assert abs(e - float(DATA[key])) < 1e-10
+    assert abs(numpy.vdot(vec, op * vec) - e) < 1e-9
+
+
+def test_sector_kernel_agrees_with_full_space_kernel_20_qubits():
+    # Hubbard 2x5 (20 qubits), 8 electrons, S_z = 0: embed a sector vector, apply the
+    # full-space K1 kernel, restrict again
+    op = models.hubbard_jw(2, 5, 1.0, 4.0)
+    lin = LinearQubitOperator(op, 20)
+    sec = SectorLinearQubitOperator(lin, n_electrons=8, sz_value=0.0)
+    assert sec.shape[0] == 210 * 210
+    rng = numpy.random.default_rng(3)
+    v = rng.normal(size=sec.shape[0]) + 1j * rng.normal(size=sec.shape[0])
+    full = sec.sector.expand_state_host(v)
+    want = sec.sector.restrict_state_host(lin * full)
+    assert helpers.close(sec * v, want, RTOL)
+    # the Hamiltonian conserves N and S_z: nothing leaks out of the sector
+    assert abs(numpy.linalg.norm(lin * full) - numpy.linalg.norm(want)) < 1e-9
+
+
+def test_hubbard_4x4_sector_is_hermitian_and_hits_known_energy():
+    # 32 qubits, 10 electrons, S_z = 0: 4368^2 = 1.9e7 amplitudes instead of 2^32.  The
+    # closed-shell 10-electron ground energy of the periodic 4x4 lattice at U = 4 is
+    # -19.58094 (the full-space 8-GPU Lanczos of config 5 returns the same number).
+    op = models.hubbard_jw(4, 4, 1.0, 4.0)
+    sec = SectorLinearQubitOperator(op, 32, n_electrons=10, sz_value=0.0)
+    dim = sec.shape[0]
+    assert dim == 4368 ** 2
+    rng = numpy.random.default_rng(7)
+    u = rng.normal(size=dim) + 1j * rng.normal(size=dim)
+    v = rng.normal(size=dim) + 1j * rng.normal(size=dim)
+    hu, hv = sec * u, sec * v
+    a, b = numpy.vdot(u, hv), numpy.vdot(hu, v)
+    assert abs(a - b) <= 1e-12 * abs(a)
+    e, vec = get_ground_state(sec)
+    assert abs(e - (-19.58094)) < 2e-5
+    assert numpy.linalg.norm(sec * vec - e * vec) < 1e-6
