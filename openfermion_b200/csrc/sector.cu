@@ -30,6 +30,10 @@ namespace ofb {
 
 constexpr int SECTOR_MAX_CON = 4;
 constexpr int SBLOCK = 256;
+#ifndef OFB_SECTOR_BATCH
+#define OFB_SECTOR_BATCH 4
+#endif
+constexpr int SECTOR_BATCH = OFB_SECTOR_BATCH;
 
 struct SectorDev {
     int lo_bits;
@@ -41,7 +45,9 @@ struct SectorDev {
     uint64_t plus[SECTOR_MAX_CON], minus[SECTOR_MAX_CON];
     int value[SECTOR_MAX_CON];
     const uint64_t *A;
+    const uint32_t *A32;  // copy of A when every position fits 32 bits (else null)
     const uint32_t *B;
+    int has_minus;        // some constraint has a non-empty minus mask
     const uint64_t *sorted;  // search mode: ascending basis states
     const uint32_t *perm;    // position of sorted[k] in the caller's order
     const uint64_t *basis;   // basis state at each position
@@ -82,43 +88,121 @@ __global__ void __launch_bounds__(SBLOCK) k_sector_enumerate(SectorDev s, uint64
         if (sector_member(s, j)) basis[sector_table_pos(s, j)] = j;
 }
 
-// out[p] = sum over segments of S(basis[p]) * in[pos(basis[p] ^ x)]
-template <bool EXPECT>
+// sigma-signed sum of `cnt` staged table entries at basis state j (two independent chains)
+template <bool Z32>
+__device__ __forceinline__ double sector_run_sum(const TermZC *tab, uint32_t cnt, uint64_t j) {
+    double a0 = 0.0, a1 = 0.0;
+    const TermZC *p = tab;
+    const TermZC *end2 = tab + (cnt & ~1u);
+    const uint32_t j32 = (uint32_t)j;
+#pragma unroll 1
+    while (p != end2) {
+        const TermZC e0 = p[0], e1 = p[1];
+        p += 2;
+        const uint32_t s0 = Z32 ? (uint32_t)__popc(j32 & (uint32_t)e0.z) : (uint32_t)__popcll(j & e0.z);
+        const uint32_t s1 = Z32 ? (uint32_t)__popc(j32 & (uint32_t)e1.z) : (uint32_t)__popcll(j & e1.z);
+        a0 += __hiloint2double(__double2hiint(e0.c) + (int)(s0 << 31), __double2loint(e0.c));
+        a1 += __hiloint2double(__double2hiint(e1.c) + (int)(s1 << 31), __double2loint(e1.c));
+    }
+    if (cnt & 1u) {
+        const TermZC e0 = p[0];
+        const uint32_t s0 = Z32 ? (uint32_t)__popc(j32 & (uint32_t)e0.z) : (uint32_t)__popcll(j & e0.z);
+        a0 += __hiloint2double(__double2hiint(e0.c) + (int)(s0 << 31), __double2loint(e0.c));
+    }
+    return a0 + a1;
+}
+
+// position of j ^ x for a member j, or -1: table mode with 32-bit fast paths
+template <bool Z32, bool POS32>
+__device__ __forceinline__ int64_t sector_pos_fast(const SectorDev &s, uint64_t jx) {
+    if (s.mode != 0) return sector_pos(s, jx);
+    if (Z32 && !s.has_minus) {
+        const uint32_t v = (uint32_t)jx;
+        bool ok = __popc(v & (uint32_t)s.plus[0]) == s.value[0];
+        if (s.n_con > 1) ok = ok && __popc(v & (uint32_t)s.plus[1]) == s.value[1];
+        if (s.n_con > 2) ok = ok && sector_member(s, jx);
+        if (!ok) return -1;
+    } else if (!sector_member(s, jx)) {
+        return -1;
+    }
+    if (POS32 && s.n_classes == 1) {
+        const uint32_t v = (uint32_t)jx;
+        return (int64_t)(uint32_t)(s.A32[v >> s.lo_bits] + s.B[v & (uint32_t)s.lo_mask]);
+    }
+    return sector_table_pos(s, jx);
+}
+
+// out[p] = sum over segments of S(basis[p]) * in[pos(basis[p] ^ x)].  The plan's chunks (<= 16
+// segments, <= 256 terms) are staged to shared memory; table reads in the term loop are
+// broadcast LDS.  Per term: LDS.128, LOP, POPC, IMAD (sign fold), DADD.
+template <bool Z32, bool POS32, bool HAS_IMAG, bool EXPECT>
 __global__ void __launch_bounds__(SBLOCK)
 k_sector_apply(SectorDev sec, const double2 *__restrict__ vin, double2 *__restrict__ vout,
-               const Segment *__restrict__ segs, const uint32_t *__restrict__ seg_term_begin,
-               uint32_t n_segs, const TermZC *__restrict__ zc_re, const TermZC *__restrict__ zc_im,
+               const Chunk *__restrict__ chunks, uint32_t n_chunks, const Segment *__restrict__ segs,
+               const TermZC *__restrict__ zc_re, const TermZC *__restrict__ zc_im,
                double2 *__restrict__ partials) {
+    __shared__ Segment s_segs[CHUNK_MAX_SEGS];
+    __shared__ TermZC s_re[CHUNK_MAX_TERMS + 2];
+    __shared__ TermZC s_im[HAS_IMAG ? CHUNK_MAX_TERMS + 2 : 1];
     const int64_t p = (int64_t)blockIdx.x * SBLOCK + threadIdx.x;
     const bool live = p < sec.dim;
     const uint64_t j = live ? sec.basis[p] : 0;
     double ar = 0.0, ai = 0.0;
-    uint64_t last_x = ~0ull;
-    int64_t q = -1;
-    double2 v = make_double2(0.0, 0.0);
-    for (uint32_t s = 0; s < n_segs; ++s) {
-        const Segment sd = segs[s];
-        if (sd.x != last_x) {  // a group may span several segments: one lookup per group
-            last_x = sd.x;
-            q = !live ? -1 : (sd.x == 0 ? p : sector_pos(sec, j ^ sd.x));
-            if (q >= 0) v = vin[q];
-        }
-        if (q < 0) continue;
-        const uint32_t kind = sd.kind_runs >> 30;
-        const uint32_t tb = seg_term_begin[s], te = tb + ((sd.kind_runs >> 8) & 0xffffu);
-        double sr = 0.0, si = 0.0;
-        for (uint32_t t = tb; t < te; ++t) {
-            const TermZC a = zc_re[t];
-            const uint32_t par = (uint32_t)__popcll(j & a.z);
-            if (kind != KIND_IMAG)
-                sr += __hiloint2double(__double2hiint(a.c) ^ (int)(par << 31), __double2loint(a.c));
-            if (kind != KIND_REAL) {
-                const double c = zc_im[t].c;
-                si += __hiloint2double(__double2hiint(c) ^ (int)(par << 31), __double2loint(c));
+    for (uint32_t c = 0; c < n_chunks; ++c) {
+        const Chunk ck = chunks[c];
+        __syncthreads();
+        {
+            const uint4 *gs = (const uint4 *)(segs + ck.seg_begin);
+            uint4 *ss = (uint4 *)s_segs;
+            for (uint32_t u = threadIdx.x; u < ck.seg_count * 2; u += SBLOCK) ss[u] = gs[u];
+            for (uint32_t u = threadIdx.x; u < ck.term_count; u += SBLOCK) {
+                s_re[u] = zc_re[ck.term_begin + u];
+                if (HAS_IMAG) s_im[u] = zc_im[ck.term_begin + u];
             }
         }
-        ar += sr * v.x - si * v.y;
-        ai += sr * v.y + si * v.x;
+        __syncthreads();
+        // Segments in batches of SECTOR_BATCH: all index-map lookups of a batch are issued
+        // before the gathers, all gathers before the sign sums, so one warp keeps several
+        // dependent load chains (table -> amplitude) in flight instead of one.
+        for (uint32_t s0 = 0; s0 < ck.seg_count; s0 += SECTOR_BATCH) {
+            int64_t q[SECTOR_BATCH];
+            double2 v[SECTOR_BATCH];
+#pragma unroll
+            for (int u = 0; u < SECTOR_BATCH; ++u) {
+                q[u] = -1;
+                if (live && s0 + u < ck.seg_count) {
+                    const uint64_t x = Z32 ? (uint64_t)s_segs[s0 + u].x_lo : s_segs[s0 + u].x;
+                    q[u] = x == 0 ? p : sector_pos_fast<Z32, POS32>(sec, j ^ x);
+                }
+            }
+#pragma unroll
+            for (int u = 0; u < SECTOR_BATCH; ++u)
+                v[u] = q[u] >= 0 ? vin[q[u]] : make_double2(0.0, 0.0);
+#pragma unroll
+            for (int u = 0; u < SECTOR_BATCH; ++u) {
+                if (q[u] < 0) continue;
+                const uint32_t kind_runs = s_segs[s0 + u].kind_runs;
+                const uint32_t cnt = (kind_runs >> 8) & 0xffffu;
+                const uint32_t tb = s_segs[s0 + u].rel_begin;
+                if (!HAS_IMAG) {
+                    const double sr = sector_run_sum<Z32>(s_re + tb, cnt, j);
+                    ar = fma(sr, v[u].x, ar);
+                    ai = fma(sr, v[u].y, ai);
+                } else {
+                    const uint32_t kind = kind_runs >> 30;
+                    if (kind != KIND_IMAG) {
+                        const double sr = sector_run_sum<Z32>(s_re + tb, cnt, j);
+                        ar = fma(sr, v[u].x, ar);
+                        ai = fma(sr, v[u].y, ai);
+                    }
+                    if (kind != KIND_REAL) {
+                        const double si = sector_run_sum<Z32>(s_im + tb, cnt, j);
+                        ar = fma(-si, v[u].y, ar);
+                        ai = fma(si, v[u].x, ai);
+                    }
+                }
+            }
+        }
     }
     if (!EXPECT) {
         if (live) vout[p] = make_double2(ar, ai);
@@ -297,6 +381,7 @@ struct ofb_sector {
     int64_t dim = 0;
     SectorDev dev{};
     uint64_t *d_A = nullptr;
+    uint32_t *d_A32 = nullptr;
     uint32_t *d_B = nullptr;
     uint64_t *d_sorted = nullptr;
     uint32_t *d_perm = nullptr;
@@ -313,6 +398,28 @@ struct ofb_sector {
 };
 
 static inline unsigned sector_grid(int64_t dim) { return (unsigned)((dim + SBLOCK - 1) / SBLOCK); }
+
+template <bool EXPECT>
+static int sector_launch_apply(ofb_plan *p, ofb_sector *s, const double2 *in, double2 *out,
+                               double2 *partials, cudaStream_t st) {
+    const unsigned grid = sector_grid(s->dim);
+    const uint32_t n_chunks = (uint32_t)p->n_chunks;
+    const bool z32 = p->n_qubits <= 32, pos32 = s->dev.A32 != nullptr;
+#define OFB_SGO(ZZ, PP, II)                                                                      \
+    k_sector_apply<ZZ, PP, II, EXPECT><<<grid, SBLOCK, 0, st>>>(s->dev, in, out, p->d_chunks,    \
+                                                                n_chunks, p->d_segs, p->d_zc,    \
+                                                                p->d_zc_im, partials)
+    if (z32) {
+        if (pos32) { if (p->has_imag) OFB_SGO(true, true, true); else OFB_SGO(true, true, false); }
+        else       { if (p->has_imag) OFB_SGO(true, false, true); else OFB_SGO(true, false, false); }
+    } else {
+        if (pos32) { if (p->has_imag) OFB_SGO(false, true, true); else OFB_SGO(false, true, false); }
+        else       { if (p->has_imag) OFB_SGO(false, false, true); else OFB_SGO(false, false, false); }
+    }
+#undef OFB_SGO
+    OFB_LAUNCH_CHECK();
+    return OFB_OK;
+}
 
 static int sector_common_checks(const ofb_plan *p, const ofb_sector *s) {
     if (!p || !s) return fail(OFB_ERR_INVALID, "NULL argument");
@@ -373,6 +480,20 @@ int ofb_sector_create_tables(int n_qubits, int lo_bits, int n_classes, uint64_t 
     d.B = s->d_B;
     d.basis = s->d_basis;
     d.dim = dim;
+    d.has_minus = 0;
+    for (int k = 0; k < n_constraints; ++k) d.has_minus |= minus_mask[k] != 0;
+    d.A32 = nullptr;
+    if (dim < (1ll << 32)) {
+        std::vector<uint32_t> a32(n_hi);
+        for (size_t k = 0; k < n_hi; ++k) a32[k] = (uint32_t)table_hi[k];
+        if ((e = cudaMalloc(&s->d_A32, n_hi * 4)) != cudaSuccess ||
+            (e = cudaMemcpy(s->d_A32, a32.data(), n_hi * 4, cudaMemcpyHostToDevice)) != cudaSuccess) {
+            int rc = cuda_fail(e, "sector tables", __FILE__, __LINE__);
+            ofb_sector_destroy(s);
+            return rc;
+        }
+        d.A32 = s->d_A32;
+    }
     if (dim > 0) {
         const uint64_t full_dim = 1ull << n_qubits;
         const unsigned grid = (unsigned)std::min<uint64_t>((full_dim + SBLOCK - 1) / SBLOCK, 148u * 64u);
@@ -443,6 +564,7 @@ int ofb_sector_destroy(ofb_sector *s) {
     if (!s) return OFB_OK;
     cudaSetDevice(s->device);
     cudaFree(s->d_A);
+    cudaFree(s->d_A32);
     cudaFree(s->d_B);
     cudaFree(s->d_sorted);
     cudaFree(s->d_perm);
@@ -481,13 +603,10 @@ int ofb_sector_apply(ofb_plan *p, ofb_sector *s, const void *d_in, void *d_out, 
     if (d_in == d_out) return fail(OFB_ERR_INVALID, "d_in and d_out must not alias");
     OFB_CUDA(cudaSetDevice(p->device));
     if (s->dim == 0) return OFB_OK;
-    const uint32_t n_segs = p->h_seg_begin.empty() ? 0 : p->h_seg_begin[p->n_groups];
     for (int c = 0; c < ncols; ++c) {
         const double2 *in = (const double2 *)d_in + (size_t)c * ld;
         double2 *out = (double2 *)d_out + (size_t)c * ld;
-        k_sector_apply<false><<<sector_grid(s->dim), SBLOCK, 0, (cudaStream_t)stream>>>(
-            s->dev, in, out, p->d_segs, p->d_seg_term_begin, n_segs, p->d_zc, p->d_zc_im, nullptr);
-        OFB_LAUNCH_CHECK();
+        if ((rc = sector_launch_apply<false>(p, s, in, out, nullptr, (cudaStream_t)stream))) return rc;
     }
     return OFB_OK;
 }
@@ -543,11 +662,9 @@ int ofb_sector_expectation(ofb_plan *p, ofb_sector *s, const void *d_state, doub
         s->partials_bytes = need;
     }
     cudaStream_t st = (cudaStream_t)stream;
-    const uint32_t n_segs = p->h_seg_begin[p->n_groups];
-    k_sector_apply<true><<<grid, SBLOCK, 0, st>>>(s->dev, (const double2 *)d_state, nullptr, p->d_segs,
-                                                  p->d_seg_term_begin, n_segs, p->d_zc, p->d_zc_im,
-                                                  (double2 *)s->d_partials);
-    OFB_LAUNCH_CHECK();
+    if ((rc = sector_launch_apply<true>(p, s, (const double2 *)d_state, nullptr,
+                                        (double2 *)s->d_partials, st)))
+        return rc;
     double *d_res = s->d_partials + 2 * (size_t)grid;
     if ((rc = reduce_partials(s->d_partials, (int64_t)grid, 2, d_res, st))) return rc;
     OFB_CUDA(cudaMemcpyAsync(s->h_pinned, d_res, 2 * sizeof(double), cudaMemcpyDeviceToHost, st));

@@ -150,11 +150,9 @@ class SectorLinearQubitOperator(scipy.sparse.linalg.LinearOperator):
         self._spin_maps = (up_index, down_index)
         self._sector = None
         if sz_value is None:
-            dim = sectors.number_sector_tables(self.n_qubits, n_electrons, 0).dim
+            dim = sectors.number_sector_dim(self.n_qubits, n_electrons)
         elif up_index is None and down_index is None:
-            tables = (sectors.sz_sector_tables(self.n_qubits, sz_value, 0) if n_electrons is None else
-                      sectors.sz_number_sector_tables(self.n_qubits, sz_value, n_electrons, 0))
-            dim = tables.dim
+            dim = sectors.sz_sector_dim(self.n_qubits, sz_value, n_electrons)
         else:
             dim = len(sectors.sz_indices_list(sz_value, self.n_qubits, n_electrons, up_index,
                                               down_index))

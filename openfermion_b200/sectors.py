@@ -78,6 +78,24 @@ def default_lo_bits(n_qubits):
     return n_qubits // 2
 
 
+def number_sector_dim(n_qubits, n_electrons):
+    return comb(n_qubits, n_electrons) if 0 <= n_electrons <= n_qubits else 0
+
+
+def sz_sector_dim(n_qubits, sz_value, n_electrons=None):
+    """len(jw_sz_indices(...)) without enumerating (same argument checks)."""
+    sz_integer = _check_sz_arguments(float(sz_value), n_qubits, n_electrons)
+    n_sites = n_qubits // 2
+    if n_electrons is not None:
+        num_up = (n_electrons + sz_integer) // 2
+        num_down = n_electrons - num_up
+        if not (0 <= num_up <= n_sites and 0 <= num_down <= n_sites):
+            return 0
+        return comb(n_sites, num_up) * comb(n_sites, num_down)
+    shift = abs(sz_integer)
+    return sum(comb(n_sites, n) * comb(n_sites, n - shift) for n in range(shift, n_sites + 1))
+
+
 class SectorTables:
     """Host description of a table-mode sector (what ofb_sector_create_tables takes)."""
 
