@@ -22,6 +22,7 @@
 // up-major S_z order a spin-up hop moves whole rows of the (up, down) grid, so the gathers
 // stay coalesced.
 #include <algorithm>
+#include <cstdlib>
 #include <cstring>
 
 #include "ofb_internal.cuh"
@@ -236,6 +237,125 @@ k_sector_apply(SectorDev sec, const double2 *__restrict__ vin, double2 *__restri
     }
 }
 
+// Fast path of k_sector_apply for the sectors that matter at scale: table mode, one class,
+// n <= 32 qubits, positions below 2^32, one or two "popcount == value" constraints (number
+// sector / S_z + number sector).  All sector parameters live in registers, positions are
+// 32-bit, and the membership test of j ^ x is two LOP/POPC/compare triples.
+struct SectorFast {
+    uint32_t plus0, plus1;
+    int value0, value1;
+    uint32_t lo_bits, lo_mask;
+    const uint32_t *A32;
+    const uint32_t *B;
+    const uint64_t *basis;
+    uint32_t dim;
+};
+constexpr uint32_t NO_POS = 0xffffffffu;
+
+template <int NCON, bool HAS_IMAG, bool EXPECT>
+__global__ void __launch_bounds__(SBLOCK)
+k_sector_apply_fast(SectorFast sec, const double2 *__restrict__ vin, double2 *__restrict__ vout,
+                    const Chunk *__restrict__ chunks, uint32_t n_chunks,
+                    const Segment *__restrict__ segs, const TermZC *__restrict__ zc_re,
+                    const TermZC *__restrict__ zc_im, double2 *__restrict__ partials) {
+    __shared__ Segment s_segs[CHUNK_MAX_SEGS];
+    __shared__ TermZC s_re[CHUNK_MAX_TERMS + 2];
+    __shared__ TermZC s_im[HAS_IMAG ? CHUNK_MAX_TERMS + 2 : 1];
+    const uint32_t p = blockIdx.x * SBLOCK + threadIdx.x;
+    const bool live = p < sec.dim;
+    const uint32_t j = live ? (uint32_t)sec.basis[p] : 0u;
+    const uint32_t plus0 = sec.plus0, plus1 = sec.plus1, lo_bits = sec.lo_bits, lo_mask = sec.lo_mask;
+    const int value0 = sec.value0, value1 = sec.value1;
+    const uint32_t *__restrict__ tab_hi = sec.A32;
+    const uint32_t *__restrict__ tab_lo = sec.B;
+    double ar = 0.0, ai = 0.0;
+    for (uint32_t c = 0; c < n_chunks; ++c) {
+        const Chunk ck = chunks[c];
+        __syncthreads();
+        {
+            const uint4 *gs = (const uint4 *)(segs + ck.seg_begin);
+            uint4 *ss = (uint4 *)s_segs;
+            for (uint32_t u = threadIdx.x; u < ck.seg_count * 2; u += SBLOCK) ss[u] = gs[u];
+            for (uint32_t u = threadIdx.x; u < ck.term_count; u += SBLOCK) {
+                s_re[u] = zc_re[ck.term_begin + u];
+                if (HAS_IMAG) s_im[u] = zc_im[ck.term_begin + u];
+            }
+        }
+        __syncthreads();
+        for (uint32_t s0 = 0; s0 < ck.seg_count; s0 += SECTOR_BATCH) {
+            uint32_t q[SECTOR_BATCH];
+            double2 v[SECTOR_BATCH];
+#pragma unroll
+            for (int u = 0; u < SECTOR_BATCH; ++u) {
+                q[u] = NO_POS;
+                if (live && s0 + u < ck.seg_count) {
+                    const uint32_t jx = j ^ s_segs[s0 + u].x_lo;
+                    bool ok = __popc(jx & plus0) == value0;
+                    if (NCON == 2) ok = ok && (__popc(jx & plus1) == value1);
+                    if (ok) q[u] = tab_hi[jx >> lo_bits] + tab_lo[jx & lo_mask];
+                }
+            }
+#pragma unroll
+            for (int u = 0; u < SECTOR_BATCH; ++u)
+                v[u] = q[u] != NO_POS ? vin[q[u]] : make_double2(0.0, 0.0);
+#pragma unroll
+            for (int u = 0; u < SECTOR_BATCH; ++u) {
+                if (q[u] == NO_POS) continue;
+                const uint32_t kind_runs = s_segs[s0 + u].kind_runs;
+                const uint32_t cnt = (kind_runs >> 8) & 0xffffu;
+                const uint32_t tb = s_segs[s0 + u].rel_begin;
+                if (!HAS_IMAG) {
+                    const double sr = sector_run_sum<true>(s_re + tb, cnt, j);
+                    ar = fma(sr, v[u].x, ar);
+                    ai = fma(sr, v[u].y, ai);
+                } else {
+                    const uint32_t kind = kind_runs >> 30;
+                    if (kind != KIND_IMAG) {
+                        const double sr = sector_run_sum<true>(s_re + tb, cnt, j);
+                        ar = fma(sr, v[u].x, ar);
+                        ai = fma(sr, v[u].y, ai);
+                    }
+                    if (kind != KIND_REAL) {
+                        const double si = sector_run_sum<true>(s_im + tb, cnt, j);
+                        ar = fma(-si, v[u].y, ar);
+                        ai = fma(si, v[u].x, ai);
+                    }
+                }
+            }
+        }
+    }
+    if (!EXPECT) {
+        if (live) vout[p] = make_double2(ar, ai);
+    } else {
+        double er = 0.0, ei = 0.0;
+        if (live) {
+            const double2 w = vin[p];
+            er = w.x * ar + w.y * ai;
+            ei = w.x * ai - w.y * ar;
+        }
+#pragma unroll
+        for (int off = 16; off > 0; off >>= 1) {
+            er += __shfl_xor_sync(0xffffffffu, er, off);
+            ei += __shfl_xor_sync(0xffffffffu, ei, off);
+        }
+        __shared__ double sm[2 * (SBLOCK / 32)];
+        const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+        if (lane == 0) {
+            sm[2 * warp] = er;
+            sm[2 * warp + 1] = ei;
+        }
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            double tr = 0.0, ti = 0.0;
+            for (int w = 0; w < SBLOCK / 32; ++w) {
+                tr += sm[2 * w];
+                ti += sm[2 * w + 1];
+            }
+            partials[blockIdx.x] = make_double2(tr, ti);
+        }
+    }
+}
+
 __global__ void __launch_bounds__(SBLOCK)
 k_sector_diagonal(SectorDev sec, double *__restrict__ out, const TermZC *__restrict__ zc, uint32_t te) {
     const int64_t p = (int64_t)blockIdx.x * SBLOCK + threadIdx.x;
@@ -405,6 +525,30 @@ static int sector_launch_apply(ofb_plan *p, ofb_sector *s, const double2 *in, do
     const unsigned grid = sector_grid(s->dim);
     const uint32_t n_chunks = (uint32_t)p->n_chunks;
     const bool z32 = p->n_qubits <= 32, pos32 = s->dev.A32 != nullptr;
+    const SectorDev &d = s->dev;
+    if (z32 && pos32 && d.mode == 0 && d.n_classes == 1 && !d.has_minus && d.n_con <= 2 &&
+        s->dim < 0xffffffffll && !getenv("OFB_SECTOR_GENERIC")) {
+        SectorFast f;
+        f.plus0 = (uint32_t)d.plus[0];
+        f.value0 = d.value[0];
+        f.plus1 = d.n_con > 1 ? (uint32_t)d.plus[1] : 0u;
+        f.value1 = d.n_con > 1 ? d.value[1] : 0;
+        f.lo_bits = (uint32_t)d.lo_bits;
+        f.lo_mask = (uint32_t)d.lo_mask;
+        f.A32 = d.A32;
+        f.B = d.B;
+        f.basis = d.basis;
+        f.dim = (uint32_t)s->dim;
+#define OFB_SFAST(NN, II)                                                                        \
+    k_sector_apply_fast<NN, II, EXPECT><<<grid, SBLOCK, 0, st>>>(f, in, out, p->d_chunks, n_chunks, \
+                                                                 p->d_segs, p->d_zc, p->d_zc_im,  \
+                                                                 partials)
+        if (d.n_con == 1) { if (p->has_imag) OFB_SFAST(1, true); else OFB_SFAST(1, false); }
+        else              { if (p->has_imag) OFB_SFAST(2, true); else OFB_SFAST(2, false); }
+#undef OFB_SFAST
+        OFB_LAUNCH_CHECK();
+        return OFB_OK;
+    }
 #define OFB_SGO(ZZ, PP, II)                                                                      \
     k_sector_apply<ZZ, PP, II, EXPECT><<<grid, SBLOCK, 0, st>>>(s->dev, in, out, p->d_chunks,    \
                                                                 n_chunks, p->d_segs, p->d_zc,    \

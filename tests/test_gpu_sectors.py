@@ -232,3 +232,16 @@ def test_hubbard_4x4_half_filling_sector_ground_state():
     assert vec.shape == (12870 ** 2,) and abs(numpy.linalg.norm(vec) - 1.0) < 1e-9
     # <psi|H|psi> through the fused sector expectation equals the eigenvalue
     assert abs(expectation(sec, vec) - e) < 1e-8
+
+
+def test_generic_sector_kernel_matches_fast_path(monkeypatch):
+    # number / S_z+number sectors normally run k_sector_apply_fast; the generic kernel (n > 32,
+    # class tables, search mode) must give the same vector on the same input
+    n, _, qop = _operators('molecular_8')
+    op = SectorLinearQubitOperator(qop, n, n_electrons=4, sz_value=0.0)
+    v = DATA['molecular_8/sz_4_0.0/v']
+    fast = op * v
+    monkeypatch.setenv('OFB_SECTOR_GENERIC', '1')
+    generic = op * v
+    assert helpers.close(generic, fast, 1e-14)
+    assert helpers.close(generic, DATA['molecular_8/sz_4_0.0/Hv'], RTOL)
