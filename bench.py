@@ -92,10 +92,10 @@ class ClockSampler:
 
 
 def workload_single(qubits):
-    from openfermion_b200 import models
+    from openfermion_b200 import hamiltonians
     if qubits % 2:
         raise SystemExit('--qubits must be even (spin orbitals)')
-    op = models.molecular_jw(qubits // 2, seed=1234)
+    op = hamiltonians.molecular_jw(qubits // 2, seed=1234)
     name = 'synthetic molecular-type JW Hamiltonian, %d qubits (random_interaction_operator(%d, expand_spin, seed=1234))' % (qubits, qubits // 2)
     return op, name
 
@@ -143,11 +143,11 @@ def run_reference(args):
         return
     sys.path.insert(0, os.path.join(ROOT, 'oracle'))
     import pauli_oracle
-    from openfermion_b200 import models
+    from openfermion_b200 import hamiltonians
     if args.gpus == 1:
         op, name = workload_single(args.qubits)
     else:
-        op, name = models.hubbard_jw(4, 4), 'Fermi-Hubbard 4x4 spinful JW, 32 qubits'
+        op, name = hamiltonians.hubbard_jw(4, 4), 'Fermi-Hubbard 4x4 spinful JW, 32 qubits'
     n = op.n_qubits
     try:
         import psutil
@@ -292,8 +292,8 @@ def run_single(args):
             d_in.free()
             d_out.free()
             plan.close()
-            from openfermion_b200 import models
-            hub = LinearQubitOperator(models.hubbard_jw(4, 4), 32)
+            from openfermion_b200 import hamiltonians
+            hub = LinearQubitOperator(hamiltonians.hubbard_jw(4, 4), 32)
             hdim = 1 << 32
             h_in, h_out = _lib.DeviceBuffer(hdim * 16), _lib.DeviceBuffer(hdim * 16)
             krylov.fill_random(hdim, 7, False, h_in.ptr)
@@ -311,6 +311,26 @@ def run_single(args):
                    'unit': UNIT, 'terms': hub.plan.n_terms, 'x_groups': hub.plan.n_groups}
             h_in.free()
             h_out.free()
+            # the same Hamiltonian restricted to its half-filled S_z = 0 sector (K7)
+            from openfermion_b200.linalg import SectorLinearQubitOperator
+            sec = SectorLinearQubitOperator(hub, n_electrons=16, sz_value=0.0)
+            sdim = sec.shape[0]
+            s_in, s_out = _lib.DeviceBuffer(sdim * 16), _lib.DeviceBuffer(sdim * 16)
+            krylov.fill_random(sdim, 9, False, s_in.ptr)
+            for _ in range(2):
+                sec.sector.apply_device(hub.plan, s_in.ptr, s_out.ptr)
+            _lib.call('ofb_event_record', ev[0], vp(None))
+            for _ in range(3):
+                sec.sector.apply_device(hub.plan, s_in.ptr, s_out.ptr)
+            _lib.call('ofb_event_record', ev[1], vp(None))
+            _lib.call('ofb_event_sync', ev[1])
+            _lib.call('ofb_event_elapsed_ms', ev[0], ev[1], ctypes.byref(hms))
+            aux['sector'] = {'workload': 'same Hamiltonian inside its (16 electrons, S_z = 0) sector: '
+                                         '%d of 2^32 amplitudes, ONE GPU' % sdim,
+                             'ms_per_step': hms.value / 3,
+                             'sector_term_amp_per_s': hub.plan.n_terms * float(sdim) * 3 / (hms.value / 1e3)}
+            s_in.free()
+            s_out.free()
         except Exception as exc:  # e.g. not enough memory on a shared box
             aux = {'error': str(exc)[:200]}
     dram = (traffic / (seconds / args.steps) / 1e9) if traffic else None

@@ -56,7 +56,7 @@ def compile_qubit_terms(terms, n_qubits):
 
 def compile_qubit_operator(operator, n_qubits):
     """compile_qubit_terms for any QubitOperator-like object; array-form operators
-    (models.MaskOperator) skip the dict walk."""
+    (hamiltonians.MaskOperator) skip the dict walk."""
     if hasattr(operator, 'index_masks'):
         x, z = operator.index_masks(n_qubits)
         return x, z, numpy.asarray(operator.coeff, dtype=numpy.complex128)

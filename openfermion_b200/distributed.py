@@ -407,7 +407,7 @@ def one_gpu_base(n_qubits):
 def bench_main(args, metric, unit, clock_sampler_cls, measured_peak):
     import torch
     import torch.distributed as dist
-    from openfermion_b200 import _lib, models
+    from openfermion_b200 import _lib, hamiltonians
     from openfermion_b200.linalg import krylov
 
     rank = int(os.environ.get('RANK', '0'))
@@ -417,11 +417,11 @@ def bench_main(args, metric, unit, clock_sampler_cls, measured_peak):
     _lib.call('ofb_set_device', ctypes.c_int(local_rank))
     n = args.dist_qubits
     if n == 32:
-        op_model, name = models.hubbard_jw(4, 4), 'Fermi-Hubbard 4x4 spinful JW (t=1, U=4, periodic), 32 qubits'
+        op_model, name = hamiltonians.hubbard_jw(4, 4), 'Fermi-Hubbard 4x4 spinful JW (t=1, U=4, periodic), 32 qubits'
     else:
         sites = n // 2
         dims = {12: (2, 3), 16: (2, 4), 20: (2, 5), 24: (3, 4), 28: (2, 7), 30: (3, 5)}[sites * 2]
-        op_model, name = models.hubbard_jw(*dims), 'Fermi-Hubbard %dx%d spinful JW, %d qubits' % (dims + (n,))
+        op_model, name = hamiltonians.hubbard_jw(*dims), 'Fermi-Hubbard %dx%d spinful JW, %d qubits' % (dims + (n,))
     mode = args.dist_mode
     op = ShardedPauliOperator(op_model, n, dist=dist, mode=mode)
     layout = op.layout

@@ -385,12 +385,12 @@ def load_molecular_data(path):
 
 def load_molecular_hamiltonian(path):
     """`MolecularData(filename=path).get_molecular_hamiltonian()` (chem/molecular_data.py:
-    1011-1039) as a models.InteractionTensor: spin-orbital expansion of the stored spatial
+    1011-1039) as a hamiltonians.InteractionTensor: spin-orbital expansion of the stored spatial
     integrals, two-body part halved; accepted by linalg.get_sparse_operator and
-    models.interaction_operator_jw."""
-    from openfermion_b200 import models
+    hamiltonians.interaction_operator_jw."""
+    from openfermion_b200 import hamiltonians
     data = load_molecular_data(path)
     if data['one_body_integrals'] is None or data['two_body_integrals'] is None:
         raise ValueError('the file holds no molecular integrals')
-    return models.molecular_hamiltonian(data['nuclear_repulsion'], data['one_body_integrals'],
+    return hamiltonians.molecular_hamiltonian(data['nuclear_repulsion'], data['one_body_integrals'],
                                         data['two_body_integrals'])

@@ -261,7 +261,7 @@ def is_fermion_operator(obj):
 
 def count_qubits(operator):
     """1 + highest index appearing in the terms (utils/operator_utils.py:143-202)."""
-    if hasattr(operator, 'index_masks'):  # models.MaskOperator: array form
+    if hasattr(operator, 'index_masks'):  # hamiltonians.MaskOperator: array form
         return operator.count_qubits()
     if not hasattr(operator, 'terms'):
         raise TypeError('Operator of invalid type.')

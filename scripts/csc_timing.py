@@ -9,7 +9,7 @@ import time
 import numpy
 
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
-from openfermion_b200 import _lib, compiler, models  # noqa: E402
+from openfermion_b200 import _lib, compiler, hamiltonians  # noqa: E402
 from openfermion_b200.plan import PauliPlan  # noqa: E402
 
 c_int, c_int64, vp = ctypes.c_int, ctypes.c_int64, ctypes.c_void_p
@@ -45,10 +45,10 @@ def run(name, op, n, mode):
 
 
 if __name__ == '__main__':
-    run('molecular dyadic', models.molecular_jw(10, seed=1234, dyadic_bits=16), 20, 0)
-    run('molecular', models.molecular_jw(7, seed=1234), 14, 1)
-    run('molecular', models.molecular_jw(7, seed=1234), 14, 0)
-    run('molecular', models.molecular_jw(8, seed=1234), 16, 1)
-    run('hubbard 2x4', models.hubbard_jw(2, 4), 16, 1)
-    run('hubbard 2x5', models.hubbard_jw(2, 5), 20, 1)
-    run('hubbard 3x4', models.hubbard_jw(3, 4), 24, 0)
+    run('molecular dyadic', hamiltonians.molecular_jw(10, seed=1234, dyadic_bits=16), 20, 0)
+    run('molecular', hamiltonians.molecular_jw(7, seed=1234), 14, 1)
+    run('molecular', hamiltonians.molecular_jw(7, seed=1234), 14, 0)
+    run('molecular', hamiltonians.molecular_jw(8, seed=1234), 16, 1)
+    run('hubbard 2x4', hamiltonians.hubbard_jw(2, 4), 16, 1)
+    run('hubbard 2x5', hamiltonians.hubbard_jw(2, 5), 20, 1)
+    run('hubbard 3x4', hamiltonians.hubbard_jw(3, 4), 24, 0)

@@ -2,16 +2,16 @@
 """Quick device-resident H|psi> timing of a few workloads (development aid)."""
 import sys, os, time
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
-from openfermion_b200 import _lib, models
+from openfermion_b200 import _lib, hamiltonians
 from openfermion_b200.linalg import LinearQubitOperator, krylov
 
 which = sys.argv[1:] or ['mol26', 'hub28']
-builders = {'mol24': lambda: models.molecular_jw(12), 'mol26': lambda: models.molecular_jw(13),
-            'mol28': lambda: models.molecular_jw(14), 'hub24': lambda: models.hubbard_jw(3, 4),
-            'hub28': lambda: models.hubbard_jw(2, 7), 'hub30': lambda: models.hubbard_jw(3, 5),
-            'rand24c': lambda: models.random_pauli_sum(24, 400, 1, True),
-            'bk24': lambda: models.molecular_jw(12, encoding='bk'), 'bk28': lambda: models.molecular_jw(14, encoding='bk'),
-            'hubbk28': lambda: models.hubbard_jw(2, 7, encoding='bk')}
+builders = {'mol24': lambda: hamiltonians.molecular_jw(12), 'mol26': lambda: hamiltonians.molecular_jw(13),
+            'mol28': lambda: hamiltonians.molecular_jw(14), 'hub24': lambda: hamiltonians.hubbard_jw(3, 4),
+            'hub28': lambda: hamiltonians.hubbard_jw(2, 7), 'hub30': lambda: hamiltonians.hubbard_jw(3, 5),
+            'rand24c': lambda: hamiltonians.random_pauli_sum(24, 400, 1, True),
+            'bk24': lambda: hamiltonians.molecular_jw(12, encoding='bk'), 'bk28': lambda: hamiltonians.molecular_jw(14, encoding='bk'),
+            'hubbk28': lambda: hamiltonians.hubbard_jw(2, 7, encoding='bk')}
 for name in which:
     op = builders[name]()
     n = op.n_qubits

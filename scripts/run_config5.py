@@ -14,7 +14,7 @@ import time
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 
-from openfermion_b200 import _lib, models  # noqa: E402
+from openfermion_b200 import _lib, hamiltonians  # noqa: E402
 from openfermion_b200.distributed import ShardedPauliOperator, init_nccl, lanczos_ground_state  # noqa: E402
 
 
@@ -30,7 +30,7 @@ def main():
     local = int(os.environ.get('LOCAL_RANK', rank))
     dist = init_nccl(local)
     _lib.call('ofb_set_device', ctypes.c_int(local))
-    op = models.hubbard_jw(args.x, args.y)
+    op = hamiltonians.hubbard_jw(args.x, args.y)
     sop = ShardedPauliOperator(op, op.n_qubits, dist=dist, mode=args.mode)
     stats = {}
     import torch

@@ -15,7 +15,7 @@ import numpy
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 
-from openfermion_b200 import _lib, models  # noqa: E402
+from openfermion_b200 import _lib, hamiltonians  # noqa: E402
 from openfermion_b200.linalg import (DavidsonOptions, LinearQubitOperator, QubitDavidson,  # noqa: E402
                                      expectation, get_ground_state, get_sparse_operator,
                                      qubit_operator_sparse)
@@ -32,7 +32,7 @@ def timed(fn):
 
 def config1():
     data = numpy.load(os.path.join(ROOT, 'tests', 'golden', 'lih_sto3g.npz'))
-    ham = models.molecular_hamiltonian(float(data['nuclear_repulsion']), data['one_body_integrals'],
+    ham = hamiltonians.molecular_hamiltonian(float(data['nuclear_repulsion']), data['one_body_integrals'],
                                        data['two_body_integrals'])
     csc, t_csc = timed(lambda: get_sparse_operator(ham))
     (e0, psi), t_gs = timed(lambda: get_ground_state(csc))
@@ -43,7 +43,7 @@ def config1():
 
 
 def config2():
-    op = models.molecular_jw(10, seed=1234, dyadic_bits=16)
+    op = hamiltonians.molecular_jw(10, seed=1234, dyadic_bits=16)
     n = 20
     csc, t_csc = timed(lambda: qubit_operator_sparse(op, n))
     rng = numpy.random.default_rng(0)
@@ -72,7 +72,7 @@ def config2():
 
 
 def config3():
-    op = models.hubbard_jw(3, 4)
+    op = hamiltonians.hubbard_jw(3, 4)
     lin = LinearQubitOperator(op, 24)
     stats = {}
     dev = krylov.as_device_operator(lin)
@@ -90,7 +90,7 @@ def config3():
 
 
 def config4(n=28, iterations=3):
-    op = models.molecular_jw(n // 2, seed=1234)
+    op = hamiltonians.molecular_jw(n // 2, seed=1234)
     numpy.random.seed(7)
     dav, t_setup = timed(lambda: QubitDavidson(op, n, DavidsonOptions(max_subspace=8, eps=1e-6)))
     guess = numpy.zeros((2**n, 1), dtype=complex)

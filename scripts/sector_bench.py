@@ -11,15 +11,15 @@ import sys
 import time
 
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
-from openfermion_b200 import _lib, models  # noqa: E402
+from openfermion_b200 import _lib, hamiltonians  # noqa: E402
 from openfermion_b200.linalg import SectorLinearQubitOperator, get_ground_state, krylov  # noqa: E402
 
 CASES = {
-    'hub34_half': (lambda: models.hubbard_jw(3, 4), 12, 0.0),
-    'hub44_10': (lambda: models.hubbard_jw(4, 4), 10, 0.0),
-    'hub44_half': (lambda: models.hubbard_jw(4, 4), 16, 0.0),
-    'mol24': (lambda: models.molecular_jw(12), 12, 0.0),
-    'mol28': (lambda: models.molecular_jw(14), 14, 0.0),
+    'hub34_half': (lambda: hamiltonians.hubbard_jw(3, 4), 12, 0.0),
+    'hub44_10': (lambda: hamiltonians.hubbard_jw(4, 4), 10, 0.0),
+    'hub44_half': (lambda: hamiltonians.hubbard_jw(4, 4), 16, 0.0),
+    'mol24': (lambda: hamiltonians.molecular_jw(12), 12, 0.0),
+    'mol28': (lambda: hamiltonians.molecular_jw(14), 14, 0.0),
 }
 
 

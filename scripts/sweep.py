@@ -7,7 +7,7 @@ import os
 import sys
 
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
-from openfermion_b200 import _lib, models  # noqa: E402
+from openfermion_b200 import _lib, hamiltonians  # noqa: E402
 from openfermion_b200.linalg import LinearQubitOperator, krylov  # noqa: E402
 
 PEAK = 6536.7
@@ -15,9 +15,9 @@ try:
     PEAK = json.load(open(os.path.join(os.path.dirname(__file__), '..', 'MEASURED_PEAKS.json')))['hbm_gbs']
 except Exception:
     pass
-cases = [('molecular', n, (lambda n=n: models.molecular_jw(n // 2, seed=1234))) for n in (20, 22, 24, 26, 28)]
-cases += [('hubbard 3x4', 24, lambda: models.hubbard_jw(3, 4)), ('hubbard 2x7', 28, lambda: models.hubbard_jw(2, 7)),
-          ('hubbard 3x5', 30, lambda: models.hubbard_jw(3, 5)), ('hubbard 4x4', 32, lambda: models.hubbard_jw(4, 4))]
+cases = [('molecular', n, (lambda n=n: hamiltonians.molecular_jw(n // 2, seed=1234))) for n in (20, 22, 24, 26, 28)]
+cases += [('hubbard 3x4', 24, lambda: hamiltonians.hubbard_jw(3, 4)), ('hubbard 2x7', 28, lambda: hamiltonians.hubbard_jw(2, 7)),
+          ('hubbard 3x5', 30, lambda: hamiltonians.hubbard_jw(3, 5)), ('hubbard 4x4', 32, lambda: hamiltonians.hubbard_jw(4, 4))]
 vp = ctypes.c_void_p
 for name, n, build in cases:
     op = build()

@@ -13,7 +13,7 @@ import torch.distributed as dist
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 
-from openfermion_b200 import _lib, models  # noqa: E402
+from openfermion_b200 import _lib, hamiltonians  # noqa: E402
 from openfermion_b200.distributed import ShardedPauliOperator, TorchComm, lanczos_ground_state  # noqa: E402
 from openfermion_b200.linalg import LinearQubitOperator, get_ground_state, krylov  # noqa: E402
 
@@ -25,9 +25,9 @@ def main():
     init_nccl(local)
     _lib.call('ofb_set_device', ctypes.c_int(local))
     ok = True
-    for name, op, n in (('hubbard_2x4', models.hubbard_jw(2, 4), 16),
-                        ('molecular_12', models.molecular_jw(6, seed=1234), 12),
-                        ('dense_complex_14', models.random_pauli_sum(14, 300, 3, True), 14)):
+    for name, op, n in (('hubbard_2x4', hamiltonians.hubbard_jw(2, 4), 16),
+                        ('molecular_12', hamiltonians.molecular_jw(6, seed=1234), 12),
+                        ('dense_complex_14', hamiltonians.random_pauli_sum(14, 300, 3, True), 14)):
         rng = numpy.random.default_rng(1)
         full = rng.normal(size=1 << n) + 1j * rng.normal(size=1 << n)
         for mode in ('nccl', 'p2p', 'ce'):
@@ -50,7 +50,7 @@ def main():
                 ok = ok and err < 1e-12
             dist.barrier()
             sop.close()
-    hub = models.hubbard_jw(2, 4)
+    hub = hamiltonians.hubbard_jw(2, 4)
     e1 = None
     if rank == 0:
         e1, _ = get_ground_state(LinearQubitOperator(hub, 16))

@@ -12,7 +12,7 @@ import torch.distributed as dist
 import torch.multiprocessing as mp
 
 import pauli_oracle as po
-from openfermion_b200 import models
+from openfermion_b200 import hamiltonians
 from openfermion_b200.distributed import ShardLayout, ShardedPauliOperator, TorchComm
 from openfermion_b200.ops import QubitOperator
 
@@ -33,9 +33,9 @@ class _HostVec:
 
 def _make_operator(kind):
     if kind == 'hubbard':
-        return models.hubbard_jw(2, 2), 8
+        return hamiltonians.hubbard_jw(2, 2), 8
     if kind == 'complex':
-        return models.random_pauli_sum(7, 40, 5, True), 7
+        return hamiltonians.random_pauli_sum(7, 40, 5, True), 7
     op = QubitOperator('X0 Y1', 0.5) + QubitOperator('Z0 Z3', -1.5) + QubitOperator('Y2 X5', 2j) \
         + QubitOperator((), 0.25)
     return op, 6
@@ -108,7 +108,7 @@ def test_sharded_matvec_over_gloo(world, kind, depth, tmp_path):
 
 
 def test_shard_layout_patterns():
-    op = models.hubbard_jw(4, 4)
+    op = hamiltonians.hubbard_jw(4, 4)
     x, _ = op.index_masks(32)
     # 4/65 groups cross at k=1 (1 pattern), 8/65 at k=2 (2), 11/65 at k=3 (4)
     for world, crossing, patterns in ((2, 4, 1), (4, 8, 2), (8, 11, 4)):

@@ -10,7 +10,7 @@ import scipy.sparse.linalg
 
 import helpers
 import pauli_oracle as po
-from openfermion_b200 import models
+from openfermion_b200 import hamiltonians
 from openfermion_b200.linalg import (Davidson, DavidsonOptions, LinearQubitOperator, QubitDavidson,
                                      SparseDavidson, append_random_vectors, generate_random_vectors,
                                      get_gap, get_ground_state, get_sparse_operator, orthonormalize,
@@ -35,8 +35,8 @@ def test_ground_state_known_answer():
     assert abs(energy2 + 2) < 1e-10 and abs(abs(numpy.vdot(expected, state2)) - 1.0) < 1e-8
 
 
-@pytest.mark.parametrize('builder', [lambda: models.hubbard_jw(2, 2), lambda: models.molecular_jw(4, 1234),
-                                     lambda: models.hubbard_jw(2, 3, 1.0, 4.0, 0.3, 0.2)])
+@pytest.mark.parametrize('builder', [lambda: hamiltonians.hubbard_jw(2, 2), lambda: hamiltonians.molecular_jw(4, 1234),
+                                     lambda: hamiltonians.hubbard_jw(2, 3, 1.0, 4.0, 0.3, 0.2)])
 def test_ground_state_matches_dense_diagonalisation(builder):
     op = builder()
     n = op.n_qubits
@@ -54,7 +54,7 @@ def test_ground_state_matches_dense_diagonalisation(builder):
 
 
 def test_ground_state_with_initial_guess():
-    op = models.hubbard_jw(2, 2)
+    op = hamiltonians.hubbard_jw(2, 2)
     want = numpy.linalg.eigvalsh(_dense(op, 8))[0]
     guess = numpy.random.rand(256) + 0j
     energy, _ = get_ground_state(LinearQubitOperator(op, 8), guess)
@@ -64,7 +64,7 @@ def test_ground_state_with_initial_guess():
 def test_lih_ground_state_energy():
     # config 1: testing/lih_integration_test.py:70-71,103-106
     data = helpers.golden('lih_sto3g.npz')
-    ham = models.molecular_hamiltonian(float(data['nuclear_repulsion']), data['one_body_integrals'],
+    ham = hamiltonians.molecular_hamiltonian(float(data['nuclear_repulsion']), data['one_body_integrals'],
                                        data['two_body_integrals'])
     csc = get_sparse_operator(ham)
     energy, state = get_ground_state(csc)
@@ -82,7 +82,7 @@ def test_get_gap():
     assert abs(get_gap(get_sparse_operator(op)) - 2.0) < 1e-9
     with pytest.raises(ValueError):
         get_gap(get_sparse_operator(QubitOperator('X0 Y1') + QubitOperator('Z0 Z1', 1j)))
-    hub = models.hubbard_jw(2, 2, 1.0, 4.0, 0.3, 0.2)
+    hub = hamiltonians.hubbard_jw(2, 2, 1.0, 4.0, 0.3, 0.2)
     vals = numpy.linalg.eigvalsh(_dense(hub, 8))
     assert abs(get_gap(LinearQubitOperator(hub, 8)) - (vals[1] - vals[0])) < 1e-8
 
@@ -212,7 +212,7 @@ def test_qubit_davidson_real_only():
 
 
 def test_qubit_davidson_hubbard_against_dense():
-    op = models.hubbard_jw(2, 2, 1.0, 4.0, 0.3, 0.2)
+    op = hamiltonians.hubbard_jw(2, 2, 1.0, 4.0, 0.3, 0.2)
     want = numpy.linalg.eigvalsh(_dense(op, 8))[:3]
     numpy.random.seed(3)
     dav = QubitDavidson(op, 8, DavidsonOptions(max_subspace=40, eps=1e-8))
@@ -274,7 +274,7 @@ def test_generate_and_append_random_vectors():
 def test_ground_state_at_particle_number_matches_dense_sector():
     from openfermion_b200.linalg import (jw_get_ground_state_at_particle_number,
                                          jw_number_restrict_operator, jw_sz_restrict_operator)
-    op = models.hubbard_jw(2, 2, 1.0, 4.0, 0.3, 0.2)
+    op = hamiltonians.hubbard_jw(2, 2, 1.0, 4.0, 0.3, 0.2)
     csc = qubit_operator_sparse(op, 8)
     dense = _dense(op, 8)
     for particles in (0, 1, 2, 4, 8):

@@ -12,7 +12,7 @@ import c_oracle
 import helpers
 import known_answers as ka
 import pauli_oracle as po
-from openfermion_b200 import compiler, models
+from openfermion_b200 import compiler, hamiltonians
 from openfermion_b200.linalg import (LinearQubitOperator, ParallelLinearQubitOperator,
                                      LinearQubitOperatorOptions, expectation, variance,
                                      get_linear_qubit_operator_diagonal, get_sparse_operator,
@@ -146,7 +146,7 @@ def test_golden_csc_pauli_route_fast_mode_contract(name, monkeypatch):
 def test_csc_exact_mode_generic_molecular_n10_bit_exact():
     """Generic (non-dyadic) coefficients, 1 519 terms per column: the scipy-order mode must
     reproduce the oracle's (= scipy's) structure and values bit for bit."""
-    op = models.molecular_jw(5, seed=1234)
+    op = hamiltonians.molecular_jw(5, seed=1234)
     got = qubit_operator_sparse(op, 10)
     want = po.qubit_operator_sparse(op.terms, 10)
     helpers.assert_csc_matches(got, want.indptr, want.indices, want.data, rtol=0)
@@ -176,7 +176,7 @@ def test_golden_csc_fermion_route(case):
 
 def test_lih_sparse_operator_matches_reference():
     data = helpers.golden('lih_sto3g.npz')
-    ham = models.molecular_hamiltonian(float(data['nuclear_repulsion']), data['one_body_integrals'],
+    ham = hamiltonians.molecular_hamiltonian(float(data['nuclear_repulsion']), data['one_body_integrals'],
                                        data['two_body_integrals'])
     mat = get_sparse_operator(ham)
     assert mat.nnz == int(data['nnz']) and str(mat.indices.dtype) == str(data['indices_dtype'])
@@ -201,15 +201,15 @@ def _state(n, seed):
 
 
 @pytest.mark.parametrize('name,builder', [
-    ('hubbard_2x4_n16', lambda: models.hubbard_jw(2, 4)),
-    ('hubbard_2x5_n20', lambda: models.hubbard_jw(2, 5)),
-    ('molecular_n12', lambda: models.molecular_jw(6, seed=1234)),
-    ('molecular_n16', lambda: models.molecular_jw(8, seed=1234)),
-    ('dense_paulis_complex_n15', lambda: models.random_pauli_sum(15, 300, 3, True)),
-    ('dense_paulis_real_n13', lambda: models.random_pauli_sum(13, 500, 4, False)),
-    ('hubbard_3x4_n24', lambda: models.hubbard_jw(3, 4)),
-    ('molecular_bk_n16', lambda: models.molecular_jw(8, seed=1234, encoding='bk')),
-    ('hubbard_2x5_bk_n20', lambda: models.hubbard_jw(2, 5, encoding='bk')),
+    ('hubbard_2x4_n16', lambda: hamiltonians.hubbard_jw(2, 4)),
+    ('hubbard_2x5_n20', lambda: hamiltonians.hubbard_jw(2, 5)),
+    ('molecular_n12', lambda: hamiltonians.molecular_jw(6, seed=1234)),
+    ('molecular_n16', lambda: hamiltonians.molecular_jw(8, seed=1234)),
+    ('dense_paulis_complex_n15', lambda: hamiltonians.random_pauli_sum(15, 300, 3, True)),
+    ('dense_paulis_real_n13', lambda: hamiltonians.random_pauli_sum(13, 500, 4, False)),
+    ('hubbard_3x4_n24', lambda: hamiltonians.hubbard_jw(3, 4)),
+    ('molecular_bk_n16', lambda: hamiltonians.molecular_jw(8, seed=1234, encoding='bk')),
+    ('hubbard_2x5_bk_n20', lambda: hamiltonians.hubbard_jw(2, 5, encoding='bk')),
 ])
 def test_matvec_and_expectation_vs_c_oracle(name, builder):
     op = builder()
@@ -227,7 +227,7 @@ def test_matvec_and_expectation_vs_c_oracle(name, builder):
 
 
 def test_matvec_accepts_reference_input_kinds():
-    op = models.hubbard_jw(2, 2)
+    op = hamiltonians.hubbard_jw(2, 2)
     lin = LinearQubitOperator(op, 8)
     ints = numpy.arange(256)
     want = po.matvec(op.terms, 8, ints)
@@ -256,7 +256,7 @@ def test_padded_qubits_and_single_qubit_and_zero_operator():
 
 def test_parallel_operator_matches_fused():
     # linear_qubit_operator_test.py:191-284 semantics on one GPU
-    op = models.hubbard_jw(2, 3)
+    op = hamiltonians.hubbard_jw(2, 3)
     qop = QubitOperator()
     qop.terms = dict(op.terms)
     par = ParallelLinearQubitOperator(qop, 12, LinearQubitOperatorOptions(processes=3))
@@ -271,8 +271,8 @@ def test_parallel_operator_matches_fused():
 
 
 # ---- size-independent properties at sizes the oracle cannot reach ---------------------------
-@pytest.mark.parametrize('builder,n', [(lambda: models.hubbard_jw(3, 4), 24),
-                                       (lambda: models.molecular_jw(11, seed=1234), 22)])
+@pytest.mark.parametrize('builder,n', [(lambda: hamiltonians.hubbard_jw(3, 4), 24),
+                                       (lambda: hamiltonians.molecular_jw(11, seed=1234), 22)])
 def test_hermiticity_and_linearity_properties(builder, n):
     lin = LinearQubitOperator(builder(), n)
     u, v = _state(n, 1), _state(n, 2)
@@ -289,7 +289,7 @@ def test_hermiticity_and_linearity_properties(builder, n):
 def test_csc_dyadic_molecular_bit_exact():
     """Dyadic coefficients: every column sum is exact, so structure and values are bit-exact
     under any summation order (SURVEY.md section 8c finding 3)."""
-    op = models.molecular_jw(5, seed=1234, dyadic_bits=16)
+    op = hamiltonians.molecular_jw(5, seed=1234, dyadic_bits=16)
     got = qubit_operator_sparse(op, 10)
     want = po.qubit_operator_sparse(op.terms, 10)
     helpers.assert_csc_matches(got, want.indptr, want.indices, want.data, rtol=0)
@@ -297,7 +297,7 @@ def test_csc_dyadic_molecular_bit_exact():
 
 def test_csc_hubbard_n12_and_n16_bit_exact():
     for dims in ((2, 3), (2, 4)):
-        op = models.hubbard_jw(*dims)
+        op = hamiltonians.hubbard_jw(*dims)
         got = qubit_operator_sparse(op, op.n_qubits)
         want = po.qubit_operator_sparse(op.terms, op.n_qubits)
         helpers.assert_csc_matches(got, want.indptr, want.indices, want.data, rtol=0)
@@ -307,7 +307,7 @@ def test_csc_generic_coefficients_residue_tolerant():
     """Generic real coefficients: scipy's per-column std::sort (unstable above 16 entries)
     decides which cancellation residues survive, so structure is compared after dropping
     entries below 64*eps*sum|c_t| on both sides; all other entries must agree to 1e-12."""
-    op = models.molecular_jw(5, seed=1234)
+    op = hamiltonians.molecular_jw(5, seed=1234)
     got = qubit_operator_sparse(op, 10).tocoo()
     want = po.qubit_operator_sparse(op.terms, 10).tocoo()
     floor = 64 * numpy.finfo(float).eps * numpy.sum(numpy.abs(op.coeff))
@@ -324,7 +324,7 @@ def test_csc_generic_coefficients_residue_tolerant():
 
 
 def test_csc_matches_matrix_free_operator_columns():
-    op = models.random_pauli_sum(7, 60, 9, True)
+    op = hamiltonians.random_pauli_sum(7, 60, 9, True)
     mat = qubit_operator_sparse(op, 7).toarray()
     cols = LinearQubitOperator(op, 7).matmat(numpy.eye(128, dtype=complex))
     assert helpers.close(mat, cols, RTOL)
@@ -336,14 +336,14 @@ def test_csc_fermion_route_equals_pauli_route_spectrum():
     case = helpers.Case(data, 'molecular_6')
     fop = helpers.fermion_operator_from(case['terms'], case['coeffs'])
     f = jordan_wigner_sparse(fop, 6).toarray()
-    q = qubit_operator_sparse(models.molecular_jw(3, seed=5), 6).toarray()
+    q = qubit_operator_sparse(hamiltonians.molecular_jw(3, seed=5), 6).toarray()
     assert numpy.allclose(numpy.linalg.eigvalsh(f), numpy.linalg.eigvalsh(q), atol=1e-10)
 
 
 # ---- sharded kernel form on one GPU (virtual ranks) -------------------------------------------
-@pytest.mark.parametrize('builder,n,world', [(lambda: models.hubbard_jw(2, 4), 16, 4),
-                                             (lambda: models.molecular_jw(6, seed=1234), 12, 8),
-                                             (lambda: models.random_pauli_sum(13, 200, 2, True), 13, 2)])
+@pytest.mark.parametrize('builder,n,world', [(lambda: hamiltonians.hubbard_jw(2, 4), 16, 4),
+                                             (lambda: hamiltonians.molecular_jw(6, seed=1234), 12, 8),
+                                             (lambda: hamiltonians.random_pauli_sum(13, 200, 2, True), 13, 2)])
 def test_virtual_rank_sharding_matches_unsharded(builder, n, world):
     """Every rank's shard is another region of one device buffer (the p2p data path with
     pointers into the same GPU): ofb_apply_groups with local_bits < n, a per-rank index_base,
@@ -414,7 +414,7 @@ def test_shards_of_states_beyond_32_qubits(n, local_bits):
 def test_diagonal_coulomb_hamiltonian_route():
     # sparse_tools_test.py:1876-1890: get_sparse_operator(DiagonalCoulombHamiltonian)
     data = helpers.golden('fermion_cases.npz')
-    dch = models.DiagonalCoulomb(data['dch/one_body'], data['dch/two_body'], complex(data['dch/constant']).real)
+    dch = hamiltonians.DiagonalCoulomb(data['dch/one_body'], data['dch/two_body'], complex(data['dch/constant']).real)
     mat = get_sparse_operator(dch)
     helpers.assert_csc_matches(mat, data['dch/indptr'], data['dch/indices'], data['dch/data'], RTOL)
 
@@ -437,7 +437,7 @@ def test_full_size_molecular_28_qubits_properties():
     from openfermion_b200.linalg import krylov
     n = 28
     dim = 1 << n
-    op = models.molecular_jw(14, seed=1234)
+    op = hamiltonians.molecular_jw(14, seed=1234)
     plan = LinearQubitOperator(op, n).plan
     assert (plan.n_terms, plan.n_groups) == (88495, 10466)
     u, v = _device_random(n, 1), _device_random(n, 2)
@@ -469,7 +469,7 @@ def test_maximum_single_gpu_size_32_qubits_columns():
     from openfermion_b200.linalg import krylov
     n = 32
     dim = 1 << n
-    op = models.hubbard_jw(4, 4)
+    op = hamiltonians.hubbard_jw(4, 4)
     x, z, c = compiler.compile_qubit_operator(op, n)
     plan = LinearQubitOperator(op, n).plan
     d_in, d_out = _lib.DeviceBuffer(dim * 16), _lib.DeviceBuffer(dim * 16)

@@ -12,7 +12,7 @@ import helpers
 import pauli_oracle
 import sector_oracle
 from helpers import fermion_operator_from, golden, qubit_operator_from
-from openfermion_b200 import models, sectors
+from openfermion_b200 import hamiltonians, sectors
 from openfermion_b200.linalg import (LinearQubitOperator, SectorLinearQubitOperator, expectation,
                                      get_ground_state, get_number_preserving_sparse_operator,
                                      jw_get_ground_state_at_particle_number,
@@ -61,7 +61,7 @@ def test_custom_spin_map_sector_uses_search_mode():
     want = DATA['lists/sz_blocked_6_0.0_2'].astype(numpy.uint64)
     sector = sectors.Sector.sz(6, 0.0, 2, up_index=lambda i: i, down_index=lambda i: i + 3)
     assert sector.mode == 1 and numpy.array_equal(sector.basis(), want)
-    hub = models.random_pauli_sum(6, 30, 3, True)
+    hub = hamiltonians.random_pauli_sum(6, 30, 3, True)
     full = pauli_oracle.qubit_operator_sparse(hub.terms, 6)
     idx = want.astype(numpy.int64)
     rng = numpy.random.default_rng(1)
@@ -175,7 +175,7 @@ def test_sector_ground_energy_by_device_lanczos(name, tag):
 def test_sector_kernel_agrees_with_full_space_kernel_20_qubits():
     # Hubbard 2x5 (20 qubits), 8 electrons, S_z = 0: embed a sector vector, apply the
     # full-space K1 kernel, restrict again
-    op = models.hubbard_jw(2, 5, 1.0, 4.0)
+    op = hamiltonians.hubbard_jw(2, 5, 1.0, 4.0)
     lin = LinearQubitOperator(op, 20)
     sec = SectorLinearQubitOperator(lin, n_electrons=8, sz_value=0.0)
     assert sec.shape[0] == 210 * 210
@@ -192,7 +192,7 @@ def test_hubbard_4x4_sector_is_hermitian_and_hits_known_energy():
     # 32 qubits, 10 electrons, S_z = 0: 4368^2 = 1.9e7 amplitudes instead of 2^32.  The
     # closed-shell 10-electron ground energy of the periodic 4x4 lattice at U = 4 is
     # -19.58094 (the full-space 8-GPU Lanczos of config 5 returns the same number).
-    op = models.hubbard_jw(4, 4, 1.0, 4.0)
+    op = hamiltonians.hubbard_jw(4, 4, 1.0, 4.0)
     sec = SectorLinearQubitOperator(op, 32, n_electrons=10, sz_value=0.0)
     dim = sec.shape[0]
     assert dim == 4368 ** 2
@@ -224,7 +224,7 @@ def test_hubbard_4x4_half_filling_sector_ground_state():
     # 32 qubits, 16 electrons, S_z = 0: 12870^2 = 1.66e8 amplitudes (2.65 GB) on one GPU, where
     # the full space needs 64 GiB per vector.  E0 of the periodic 4x4 lattice at U = 4, half
     # filling: -13.62185 (exact-diagonalisation literature value, -0.85137 per site).
-    op = models.hubbard_jw(4, 4, 1.0, 4.0)
+    op = hamiltonians.hubbard_jw(4, 4, 1.0, 4.0)
     sec = SectorLinearQubitOperator(op, 32, n_electrons=16, sz_value=0.0)
     assert sec.shape[0] == 12870 ** 2
     e, vec = jw_get_ground_state_at_particle_number(op, 16, sz_value=0.0, expand=False)

@@ -11,7 +11,7 @@ import pytest
 
 import pauli_oracle
 from helpers import golden
-from openfermion_b200 import hdf5, models
+from openfermion_b200 import hdf5, hamiltonians
 from openfermion_b200.linalg import sparse_tools as st
 
 DATA_DIR = '/root/reference/src/openfermion/testing/data'

@@ -9,7 +9,7 @@ import pytest
 
 import helpers
 import pauli_oracle as po
-from openfermion_b200 import _lib, compiler, models
+from openfermion_b200 import _lib, compiler, hamiltonians
 from openfermion_b200.ops import FermionOperator, QubitOperator, count_qubits
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
@@ -143,12 +143,12 @@ def test_dead_fermion_terms_emit_nothing():
 
 # ---- generators -----------------------------------------------------------------------
 @pytest.mark.parametrize('name,builder', [
-    ('hubbard_2x2_jw', lambda: models.hubbard_jw(2, 2, 1.0, 4.0)),
-    ('hubbard_2x2_mu_h_jw', lambda: models.hubbard_jw(2, 2, 1.0, 4.0, 0.3, 0.2)),
-    ('hubbard_2x3_jw', lambda: models.hubbard_jw(2, 3, 1.0, 4.0)),
-    ('molecular_8_jw', lambda: models.molecular_jw(4, seed=1234)),
-    ('hubbard_2x2_bk', lambda: models.hubbard_jw(2, 2, 1.0, 4.0, encoding='bk')),
-    ('molecular_6_bk', lambda: models.molecular_jw(3, seed=5, encoding='bk')),
+    ('hubbard_2x2_jw', lambda: hamiltonians.hubbard_jw(2, 2, 1.0, 4.0)),
+    ('hubbard_2x2_mu_h_jw', lambda: hamiltonians.hubbard_jw(2, 2, 1.0, 4.0, 0.3, 0.2)),
+    ('hubbard_2x3_jw', lambda: hamiltonians.hubbard_jw(2, 3, 1.0, 4.0)),
+    ('molecular_8_jw', lambda: hamiltonians.molecular_jw(4, seed=1234)),
+    ('hubbard_2x2_bk', lambda: hamiltonians.hubbard_jw(2, 2, 1.0, 4.0, encoding='bk')),
+    ('molecular_6_bk', lambda: hamiltonians.molecular_jw(3, seed=5, encoding='bk')),
 ])
 def test_generators_reproduce_reference_operators(name, builder):
     data = helpers.golden('qubit_cases.npz')
@@ -160,13 +160,13 @@ def test_generators_reproduce_reference_operators(name, builder):
 
 def test_baseline_config_statistics():
     # T and G of the BASELINE.json configs
-    for op, terms, groups in ((models.hubbard_jw(3, 4), 133, 49), (models.hubbard_jw(4, 4), 177, 65),
-                              (models.molecular_jw(10), 22351, 2536)):
+    for op, terms, groups in ((hamiltonians.hubbard_jw(3, 4), 133, 49), (hamiltonians.hubbard_jw(4, 4), 177, 65),
+                              (hamiltonians.molecular_jw(10), 22351, 2536)):
         assert (len(op), op.n_distinct_x()) == (terms, groups)
 
 
 def test_mask_operator_index_masks_match_compiler():
-    op = models.molecular_jw(3, seed=5)
+    op = hamiltonians.molecular_jw(3, seed=5)
     x1, z1 = op.index_masks()
     x2, z2, c2 = compiler.compile_qubit_terms(op.terms, op.n_qubits)
     assert numpy.array_equal(x1, x2) and numpy.array_equal(z1, z2)
@@ -176,7 +176,7 @@ def test_mask_operator_index_masks_match_compiler():
 def test_spin_orbital_tensors_layout():
     rng = numpy.random.default_rng(0)
     one, two = rng.normal(size=(2, 2)), rng.normal(size=(2, 2, 2, 2))
-    o, t = models.spin_orbital_tensors(one, two)
+    o, t = hamiltonians.spin_orbital_tensors(one, two)
     assert o[2, 0] == one[1, 0] and o[3, 1] == one[1, 0] and o[0, 1] == 0
     assert t[0, 3, 1, 2] == two[0, 1, 0, 1] and t[1, 2, 0, 3] == two[0, 1, 0, 1]
     assert t[2, 2, 0, 0] == two[1, 1, 0, 0] and t[0, 1, 0, 1] == 0

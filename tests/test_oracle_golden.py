@@ -8,7 +8,7 @@ import c_oracle
 import pauli_oracle as po
 import helpers
 import known_answers as ka
-from openfermion_b200 import compiler, models
+from openfermion_b200 import compiler, hamiltonians
 from openfermion_b200.ops import QubitOperator, count_qubits
 
 
@@ -101,7 +101,7 @@ def test_ground_state_known_answer():
 def test_lih_ground_state_matches_file_energy():
     # testing/lih_integration_test.py:70-71,103-106
     data = helpers.golden('lih_sto3g.npz')
-    ham = models.molecular_hamiltonian(float(data['nuclear_repulsion']), data['one_body_integrals'],
+    ham = hamiltonians.molecular_hamiltonian(float(data['nuclear_repulsion']), data['one_body_integrals'],
                                        data['two_body_integrals'])
     from openfermion_b200.linalg.sparse_tools import _tensor_fermion_terms
     fop = _tensor_fermion_terms(ham)

@@ -163,9 +163,9 @@ def test_normal_ordered_known_answers():
 
 
 def test_sector_linear_operator_shape_needs_no_gpu():
-    from openfermion_b200 import models
+    from openfermion_b200 import hamiltonians
     from openfermion_b200.linalg import SectorLinearQubitOperator
-    hub = models.hubbard_jw(2, 2)
+    hub = hamiltonians.hubbard_jw(2, 2)
     assert SectorLinearQubitOperator(hub, n_electrons=4).shape == (70, 70)
     assert SectorLinearQubitOperator(hub, n_electrons=4, sz_value=0).shape == (36, 36)
     assert SectorLinearQubitOperator(hub, sz_value=0.5).shape == (56, 56)
