@@ -191,6 +191,53 @@ def get_gap(sparse_operator, initial_guess=None):
     return abs(values[1] - values[0])
 
 
+def jw_configuration_state(occupied_orbitals, n_qubits):
+    """Basis state with the given orbitals occupied, float64[2^n] (sparse_tools.py:250-264)."""
+    one_index = sum(2 ** (n_qubits - 1 - i) for i in occupied_orbitals)
+    basis_vector = numpy.zeros(2**n_qubits, dtype=float)
+    basis_vector[one_index] = 1
+    return basis_vector
+
+
+def jw_hartree_fock_state(n_electrons, n_orbitals):
+    """Hartree-Fock determinant in the JW encoding (sparse_tools.py:267-270)."""
+    return jw_configuration_state(range(n_electrons), n_orbitals)
+
+
+def get_density_matrix(states, probabilities):
+    """sum_k p_k |psi_k><psi_k| as scipy CSC (sparse_tools.py:557-563)."""
+    n_qubits = states[0].shape[0]
+    density_matrix = scipy.sparse.csc_matrix((n_qubits, n_qubits), dtype=complex)
+    for state, probability in zip(states, probabilities):
+        state = scipy.sparse.csc_matrix(state.reshape((len(state), 1)))
+        density_matrix = density_matrix + probability * state * state.getH()
+    return density_matrix
+
+
+def _is_hermitian_sparse(operator):
+    difference = operator - operator.getH()
+    return difference.nnz == 0 or numpy.max(numpy.abs(difference.data)) <= ops.EQ_TOLERANCE
+
+
+def sparse_eigenspectrum(sparse_operator):
+    """Dense diagonalisation of a materialised operator, sorted (sparse_tools.py:615-626)."""
+    dense_operator = sparse_operator.toarray()
+    if _is_hermitian_sparse(scipy.sparse.csc_matrix(sparse_operator)):
+        spectrum = numpy.linalg.eigvalsh(dense_operator)
+    else:
+        spectrum = numpy.linalg.eigvals(dense_operator)
+    return numpy.sort(spectrum)
+
+
+def eigenspectrum(operator, n_qubits=None):
+    """Full spectrum of a symbolic operator: device CSC build, then the reference's dense
+    solve (sparse_tools.py:590-612; cubic in 2^n, small systems only)."""
+    names = {c.__name__ for c in type(operator).__mro__}
+    if names & {'BosonOperator', 'QuadOperator'}:
+        raise TypeError('Operator of invalid type.')
+    return sparse_eigenspectrum(get_sparse_operator(operator, n_qubits))
+
+
 def inner_product(state_1, state_2):
     """conj(state_1) . state_2 (sparse_tools.py:1098-1100)."""
     return numpy.dot(state_1.conjugate(), state_2)

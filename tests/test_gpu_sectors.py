@@ -245,3 +245,55 @@ def test_generic_sector_kernel_matches_fast_path(monkeypatch):
     generic = op * v
     assert helpers.close(generic, fast, 1e-14)
     assert helpers.close(generic, DATA['molecular_8/sz_4_0.0/Hv'], RTOL)
+
+
+def _restricted_dense(terms, n_qubits, basis):
+    """Independent host evaluation of P H P on a short basis list: every Pauli string applied to
+    every basis ket with integer arithmetic (qubit q = index bit n-1-q)."""
+    position = {int(b): k for k, b in enumerate(basis)}
+    out = numpy.zeros((len(basis), len(basis)), dtype=complex)
+    for term, coefficient in terms.items():
+        x = z = 0
+        n_y = 0
+        for qubit, action in term:
+            bit = 1 << (n_qubits - 1 - qubit)
+            if action in 'XY':
+                x |= bit
+            if action in 'YZ':
+                z |= bit
+            n_y += action == 'Y'
+        for col, ket in enumerate(basis):
+            ket = int(ket)
+            row = position.get(ket ^ x)
+            if row is not None:
+                # P|ket> = i^{n_y} (-1)^{popc(ket & z)} |ket ^ x>
+                out[row, col] += coefficient * (1j ** n_y) * (-1) ** bin(ket & z).count('1')
+    return out
+
+
+def test_sectors_beyond_32_qubits_use_the_64_bit_kernel():
+    # 1 x 17 Hubbard chain = 34 qubits, 2 electrons, S_z = 0: 289 amplitudes out of 2^34
+    op = hamiltonians.hubbard_jw(1, 17, 1.0, 4.0)
+    sec = SectorLinearQubitOperator(op, 34, n_electrons=2, sz_value=0.0)
+    assert sec.shape == (289, 289)
+    basis = sec.indices()
+    assert list(basis) == sector_oracle.jw_sz_indices(0.0, 34, 2)
+    dense = _restricted_dense(op.terms, 34, basis)
+    assert numpy.allclose(dense, dense.conj().T)
+    got = sec.matmat(numpy.eye(289, dtype=complex))
+    assert helpers.close(got, dense, RTOL)
+    assert helpers.close(sec.diagonal(), numpy.diag(dense).real, RTOL)
+    e, _ = get_ground_state(sec)
+    assert abs(e - numpy.linalg.eigvalsh(dense)[0]) < 1e-10
+    number = SectorLinearQubitOperator(op, 34, n_electrons=1)
+    assert number.shape == (34, 34) and list(number.indices()) == sector_oracle.jw_number_indices(1, 34)
+    dense1 = _restricted_dense(op.terms, 34, number.indices())
+    assert helpers.close(number.matmat(numpy.eye(34, dtype=complex)), dense1, RTOL)
+
+
+def test_eigenspectrum_of_symbolic_operators():
+    from openfermion_b200.linalg import eigenspectrum
+    n, fop, qop = _operators('hubbard_2x2')
+    want = numpy.linalg.eigvalsh(pauli_oracle.jordan_wigner_sparse(fop.terms, n).toarray())
+    assert numpy.allclose(eigenspectrum(fop, n), want, atol=1e-10)
+    assert numpy.allclose(eigenspectrum(qop, n), want, atol=1e-10)

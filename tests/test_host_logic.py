@@ -6,6 +6,7 @@ import re
 
 import numpy
 import pytest
+import scipy.sparse
 
 import helpers
 import pauli_oracle as po
@@ -190,7 +191,12 @@ def test_linalg_api_surface_and_errors():
                  'generate_linear_qubit_operator', 'get_linear_qubit_operator_diagonal', 'expectation',
                  'variance', 'get_ground_state', 'get_gap', 'inner_product', 'Davidson',
                  'DavidsonOptions', 'QubitDavidson', 'SparseDavidson', 'DavidsonError',
-                 'generate_random_vectors', 'append_random_vectors', 'orthonormalize']:
+                 'generate_random_vectors', 'append_random_vectors', 'orthonormalize',
+                 'jw_number_indices', 'jw_sz_indices', 'jw_number_restrict_operator',
+                 'jw_sz_restrict_operator', 'jw_number_restrict_state', 'jw_sz_restrict_state',
+                 'jw_get_ground_state_at_particle_number', 'get_number_preserving_sparse_operator',
+                 'jw_configuration_state', 'jw_hartree_fock_state', 'get_density_matrix',
+                 'eigenspectrum', 'sparse_eigenspectrum', 'SectorLinearQubitOperator']:
         assert hasattr(linalg, name), name
     with pytest.raises(ValueError):
         linalg.LinearQubitOperator(QubitOperator('X3'), 1)
@@ -218,6 +224,24 @@ def test_linalg_api_surface_and_errors():
     assert len(par.linear_operators) == len(par.qubit_operator_groups)
     assert isinstance(linalg.generate_linear_qubit_operator(QubitOperator('X0')), linalg.LinearQubitOperator)
     assert linalg.inner_product(numpy.array([1j, 0]), numpy.array([1j, 0])) == 1
+
+
+def test_small_state_helpers_follow_reference():
+    # sparse_tools_test.py known answers: jw_hartree_fock_state(2, 4) is |1100> = index 12
+    from openfermion_b200 import linalg
+    hf = linalg.jw_hartree_fock_state(2, 4)
+    assert hf.dtype == numpy.float64 and list(hf.nonzero()[0]) == [12] and hf[12] == 1.0
+    conf = linalg.jw_configuration_state([0, 3], 4)
+    assert list(conf.nonzero()[0]) == [9]
+    rho = linalg.get_density_matrix([numpy.array([1, 0]), numpy.array([0, 1])], [0.25, 0.75])
+    assert scipy.sparse.isspmatrix_csc(rho) and numpy.allclose(rho.toarray(), numpy.diag([0.25, 0.75]))
+    spectrum = linalg.sparse_eigenspectrum(scipy.sparse.csc_matrix(numpy.array([[2.0, 1j], [-1j, 2.0]])))
+    assert numpy.allclose(spectrum, [1.0, 3.0])
+    nonherm = linalg.sparse_eigenspectrum(scipy.sparse.csc_matrix(numpy.array([[0.0, 1.0], [0.0, 0.0]])))
+    assert numpy.allclose(nonherm, [0.0, 0.0])
+    restricted = linalg.jw_number_restrict_state(numpy.arange(16), 2)
+    assert list(restricted) == [3, 5, 9, 6, 10, 12]
+    assert list(linalg.jw_sz_restrict_state(numpy.arange(16), 0.0, 2)) == linalg.jw_sz_indices(0.0, 4, 2)
 
 
 # ---- sector helpers -------------------------------------------------------------
