@@ -192,16 +192,21 @@ def _collect(n_qubits, pieces, tol=EQ_TOLERANCE):
     x = numpy.concatenate([p[0] for p in pieces])
     z = numpy.concatenate([p[1] for p in pieces])
     c = numpy.concatenate([p[2] for p in pieces])
-    if n_qubits > 32:
-        raise ValueError('generators support at most 32 qubits')
-    key = (x << numpy.uint64(32)) | z
-    uniq, inverse = numpy.unique(key, return_inverse=True)
-    re = numpy.bincount(inverse, weights=c.real, minlength=len(uniq))
-    im = numpy.bincount(inverse, weights=c.imag, minlength=len(uniq))
+    if n_qubits > 64:
+        raise ValueError('generators support at most 64 qubits')
+    if n_qubits <= 32:
+        key = (x << numpy.uint64(32)) | z
+        uniq, inverse = numpy.unique(key, return_inverse=True)
+        ux, uz = uniq >> numpy.uint64(32), uniq & numpy.uint64(0xFFFFFFFF)
+    else:  # same (x, z) lexicographic order, two-column form
+        pairs, inverse = numpy.unique(numpy.stack([x, z], axis=1), axis=0, return_inverse=True)
+        inverse = inverse.reshape(-1)
+        ux, uz = pairs[:, 0], pairs[:, 1]
+    re = numpy.bincount(inverse, weights=c.real, minlength=len(ux))
+    im = numpy.bincount(inverse, weights=c.imag, minlength=len(ux))
     total = re + 1j * im
     keep = numpy.abs(total) >= tol
-    uniq, total = uniq[keep], total[keep]
-    return MaskOperator(n_qubits, uniq >> numpy.uint64(32), uniq & numpy.uint64(0xFFFFFFFF), total)
+    return MaskOperator(n_qubits, ux[keep], uz[keep], total[keep])
 
 
 # ----------------------------------------------------------------------------
