@@ -327,9 +327,24 @@ def sector_cases():
     print('sector_cases:', len(lists), 'lists,', len(names), 'operators,', len(np_cases), 'number-preserving cases')
 
 
+def operator_file_cases():
+    """Plain-text operator files written by the reference's save_operator
+    (utils/operator_utils.py:309-360), for openfermion_b200/operator_files.py."""
+    from openfermion.utils.operator_utils import save_operator, load_operator
+    fop = fermi_hubbard(2, 2, 1.0, 4.0, 0.3, 0.2)
+    qop = jordan_wigner(fop) + QubitOperator('X0 Y3', 0.5 - 0.25j)
+    for name, op in (('operator_file_fermion', fop), ('operator_file_qubit', qop)):
+        path = os.path.join(GOLDEN, name + '.data')
+        if os.path.exists(path):
+            os.remove(path)
+        save_operator(op, name, GOLDEN, plain_text=True)
+        assert load_operator(name, GOLDEN, plain_text=True) == op
+    print('operator files written')
+
+
 if __name__ == '__main__':
     os.makedirs(GOLDEN, exist_ok=True)
-    which = sys.argv[1:] or ['qubit', 'fermion', 'lih', 'sector']
+    which = sys.argv[1:] or ['qubit', 'fermion', 'lih', 'sector', 'files']
     if 'qubit' in which:
         qubit_cases()
     if 'fermion' in which:
@@ -338,3 +353,5 @@ if __name__ == '__main__':
         lih_case()
     if 'sector' in which:
         sector_cases()
+    if 'files' in which:
+        operator_file_cases()
