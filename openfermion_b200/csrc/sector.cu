@@ -81,12 +81,28 @@ __device__ __forceinline__ int64_t sector_pos(const SectorDev &s, uint64_t j) {
     return (lo < s.dim && s.sorted[lo] == j) ? (int64_t)s.perm[lo] : -1;
 }
 
-// table mode: enumerate all 2^n indices once and drop each member at its position
-__global__ void __launch_bounds__(SBLOCK) k_sector_enumerate(SectorDev s, uint64_t full_dim,
+// table mode: enumerate the members once and drop each at its position.  One thread per high
+// half: halves that cannot be completed to a member (plus-only constraints: too many bits set
+// already, or too few low bits left to reach the count) are skipped, so dilute sectors of 40
+// qubits cost O(feasible halves * 2^lo_bits) instead of 2^40; the low-half loop reads the
+// low table warp-uniformly.
+__global__ void __launch_bounds__(SBLOCK) k_sector_enumerate(SectorDev s, uint64_t n_hi,
                                                              uint64_t *__restrict__ basis) {
-    const uint64_t stride = (uint64_t)gridDim.x * SBLOCK;
-    for (uint64_t j = (uint64_t)blockIdx.x * SBLOCK + threadIdx.x; j < full_dim; j += stride)
+    const uint64_t hi = (uint64_t)blockIdx.x * SBLOCK + threadIdx.x;
+    if (hi >= n_hi) return;
+    const uint64_t hi_part = hi << s.lo_bits;
+    if (!s.has_minus) {
+        for (int k = 0; k < s.n_con; ++k) {
+            const int have = __popcll(hi_part & s.plus[k]);
+            const int room = __popcll(s.plus[k] & s.lo_mask);
+            if (have > s.value[k] || s.value[k] - have > room) return;
+        }
+    }
+    const uint64_t n_lo = s.lo_mask + 1;
+    for (uint64_t lo = 0; lo < n_lo; ++lo) {
+        const uint64_t j = hi_part | lo;
         if (sector_member(s, j)) basis[sector_table_pos(s, j)] = j;
+    }
 }
 
 // sigma-signed sum of `cnt` staged table entries at basis state j (two independent chains)
@@ -639,11 +655,11 @@ int ofb_sector_create_tables(int n_qubits, int lo_bits, int n_classes, uint64_t 
         d.A32 = s->d_A32;
     }
     if (dim > 0) {
-        const uint64_t full_dim = 1ull << n_qubits;
-        const unsigned grid = (unsigned)std::min<uint64_t>((full_dim + SBLOCK - 1) / SBLOCK, 148u * 64u);
+        const uint64_t n_hi_states = 1ull << (n_qubits - lo_bits);
+        const unsigned grid = (unsigned)((n_hi_states + SBLOCK - 1) / SBLOCK);
         // poison first so that a wrong table (a position never written) is caught by the tests
         cudaMemset(s->d_basis, 0xff, dim * 8);
-        k_sector_enumerate<<<grid, SBLOCK>>>(d, full_dim, s->d_basis);
+        k_sector_enumerate<<<grid, SBLOCK>>>(d, n_hi_states, s->d_basis);
         g_launches.fetch_add(1);
         if ((e = cudaGetLastError()) != cudaSuccess || (e = cudaDeviceSynchronize()) != cudaSuccess) {
             int rc = cuda_fail(e, "k_sector_enumerate", __FILE__, __LINE__);

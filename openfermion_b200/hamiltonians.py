@@ -327,12 +327,13 @@ def random_interaction_tensors(n_orbitals, seed=None, dyadic_bits=None):
     return constant, one_spin, two_spin
 
 
-def interaction_operator_jw(constant, one_body, two_body, encoding='jw'):
+def interaction_operator_jw(constant, one_body, two_body, encoding='jw', n_qubits=None):
     """JW of constant + sum h_pq p^ q + sum h_pqrs p^ q^ r s (InteractionOperator convention,
     ops/representations/interaction_operator.py) as a MaskOperator."""
     one_body = numpy.asarray(one_body)
     two_body = numpy.asarray(two_body)
-    n_qubits = one_body.shape[0]
+    if n_qubits is None:
+        n_qubits = one_body.shape[0]
     tables = _tables_for(encoding, n_qubits)
     pieces = []
     if constant:

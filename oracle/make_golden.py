@@ -244,6 +244,9 @@ def sector_cases():
         cases[name + '/qubit_terms'] = qs
         cases[name + '/qubit_coeffs'] = qc
         cases[name + '/qubit_coeff_is_complex'] = qic
+        bs, bc, _ = pack_terms(bravyi_kitaev(fop).terms, qubit_term_str)
+        cases[name + '/bk_terms'] = bs
+        cases[name + '/bk_coeffs'] = bc
         full_f = get_sparse_operator(fop, n)
         full_q = get_sparse_operator(qop, n)
         tags = []

@@ -271,24 +271,31 @@ def _restricted_dense(terms, n_qubits, basis):
     return out
 
 
-def test_sectors_beyond_32_qubits_use_the_64_bit_kernel():
-    # 1 x 17 Hubbard chain = 34 qubits, 2 electrons, S_z = 0: 289 amplitudes out of 2^34
-    op = hamiltonians.hubbard_jw(1, 17, 1.0, 4.0)
-    sec = SectorLinearQubitOperator(op, 34, n_electrons=2, sz_value=0.0)
-    assert sec.shape == (289, 289)
+@pytest.mark.parametrize('sites', [17, 20])
+def test_sectors_beyond_32_qubits_use_the_64_bit_kernel(sites):
+    # 1 x 17 / 1 x 20 Hubbard chains = 34 / 40 qubits, 2 electrons, S_z = 0: sites^2 amplitudes
+    # out of 2^34 / 2^40 (the enumeration skips high halves that cannot reach the counts)
+    n = 2 * sites
+    op = hamiltonians.hubbard_jw(1, sites, 1.0, 4.0)
+    sec = SectorLinearQubitOperator(op, n, n_electrons=2, sz_value=0.0)
+    dim = sites * sites
+    assert sec.shape == (dim, dim)
     basis = sec.indices()
-    assert list(basis) == sector_oracle.jw_sz_indices(0.0, 34, 2)
-    dense = _restricted_dense(op.terms, 34, basis)
+    assert list(basis) == sector_oracle.jw_sz_indices(0.0, n, 2)
+    dense = _restricted_dense(op.terms, n, basis)
     assert numpy.allclose(dense, dense.conj().T)
-    got = sec.matmat(numpy.eye(289, dtype=complex))
+    got = sec.matmat(numpy.eye(dim, dtype=complex))
     assert helpers.close(got, dense, RTOL)
     assert helpers.close(sec.diagonal(), numpy.diag(dense).real, RTOL)
     e, _ = get_ground_state(sec)
     assert abs(e - numpy.linalg.eigvalsh(dense)[0]) < 1e-10
-    number = SectorLinearQubitOperator(op, 34, n_electrons=1)
-    assert number.shape == (34, 34) and list(number.indices()) == sector_oracle.jw_number_indices(1, 34)
-    dense1 = _restricted_dense(op.terms, 34, number.indices())
-    assert helpers.close(number.matmat(numpy.eye(34, dtype=complex)), dense1, RTOL)
+    number = SectorLinearQubitOperator(op, n, n_electrons=1)
+    assert number.shape == (n, n) and list(number.indices()) == sector_oracle.jw_number_indices(1, n)
+    dense1 = _restricted_dense(op.terms, n, number.indices())
+    assert helpers.close(number.matmat(numpy.eye(n, dtype=complex)), dense1, RTOL)
+    # the restricted CSC of the same symbolic operator
+    csc = jw_sz_restrict_operator(op, 0.0, 2, n)
+    assert csc.shape == (dim, dim) and helpers.close(csc.toarray(), dense, RTOL)
 
 
 def test_eigenspectrum_of_symbolic_operators():

@@ -95,3 +95,18 @@ def test_unsupported_files_fail_loudly(tmp_path):
     newer.write_bytes(bytes(raw))
     with pytest.raises(hdf5.Hdf5FormatError, match='superblock version 2'):
         hdf5.File(str(newer))
+
+
+def test_reduced_density_matrix_files():
+    # testing/{tqdm,phdm}_*.hdf5: one contiguous float64 dataset each
+    base = os.path.dirname(DATA_DIR)
+    for name, n in (('H2_sto-3g_singlet_1.4', 4), ('H2_6-31g_singlet_0.75', 8),
+                    ('H1-Li1_sto-3g_singlet_1.45', 12)):
+        tq = hdf5.File(os.path.join(base, 'tqdm_{}.hdf5'.format(name)))['tqdm'][...]
+        ph = hdf5.File(os.path.join(base, 'phdm_{}.hdf5'.format(name)))['phdm'][...]
+        assert tq.shape == ph.shape == (n, n, n, n) and tq.dtype == numpy.float64
+        # two-hole RDM: antisymmetric in its first index pair, trace fixed by the hole count
+        assert numpy.abs(tq + tq.transpose(1, 0, 2, 3)).max() < 1e-12
+        n_electrons = {4: 2, 8: 2, 12: 4}[n]
+        holes = n - n_electrons
+        assert abs(numpy.einsum('pqqp', tq) - holes * (holes - 1)) < 1e-8
