@@ -25,9 +25,9 @@
 namespace ofb {
 
 constexpr int BLOCK = 1 << OFB_APPLY_BLOCK_BITS;
-constexpr int R8 = 8;
+constexpr int R8 = 1 << CLASS_BITS;  // amplitudes per thread (8, or 16 with OFB_APPLY_CLASS_BITS=4)
 constexpr int TILE8 = BLOCK * R8;
-constexpr int TILE8_BITS = OFB_APPLY_BLOCK_BITS + 3;
+constexpr int TILE8_BITS = OFB_APPLY_BLOCK_BITS + CLASS_BITS;
 static_assert(BLOCK == (1 << CLASS_SHIFT), "class bits must sit right above the thread index");
 
 __device__ __forceinline__ double signed_coeff(double c, uint32_t parity) {
@@ -98,7 +98,19 @@ __device__ __forceinline__ void apply_class_dyn(uint32_t w, double a, const doub
         case 4: apply_class<4, IMAG>(a, v, ar, ai); break;
         case 5: apply_class<5, IMAG>(a, v, ar, ai); break;
         case 6: apply_class<6, IMAG>(a, v, ar, ai); break;
+#if OFB_APPLY_CLASS_BITS == 4
+        case 7: apply_class<7, IMAG>(a, v, ar, ai); break;
+        case 8: apply_class<8, IMAG>(a, v, ar, ai); break;
+        case 9: apply_class<9, IMAG>(a, v, ar, ai); break;
+        case 10: apply_class<10, IMAG>(a, v, ar, ai); break;
+        case 11: apply_class<11, IMAG>(a, v, ar, ai); break;
+        case 12: apply_class<12, IMAG>(a, v, ar, ai); break;
+        case 13: apply_class<13, IMAG>(a, v, ar, ai); break;
+        case 14: apply_class<14, IMAG>(a, v, ar, ai); break;
+        default: apply_class<15, IMAG>(a, v, ar, ai); break;
+#else
         default: apply_class<7, IMAG>(a, v, ar, ai); break;
+#endif
     }
 }
 
@@ -117,7 +129,7 @@ __device__ __forceinline__ void segment_pass(const TermZC *tab, uint32_t runs, u
     for (uint32_t k = 0; k < runs; ++k) {
         const uint32_t cnt = (uint32_t)cnts & 0xffu;
         const double a = run_sum<Z32>(tab, cnt, j_lo, base_hi);
-        apply_class_dyn<IMAG>(ids & 7u, a, v, ar, ai);
+        apply_class_dyn<IMAG>(ids & 0xfu, a, v, ar, ai);
         tab += cnt;
         cnts >>= 8;
         ids >>= 4;

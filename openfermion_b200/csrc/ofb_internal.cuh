@@ -39,16 +39,23 @@ struct __align__(16) GroupDesc {  // scatter-form groups of the CSC builder
     uint32_t count;  // bits 0..29 row count
 };
 // Gather-form execution unit: at most 255 terms of one x-group, sorted by the "class"
-// w = (z >> CLASS_SHIFT) & 7, i.e. by the three z bits that distinguish the 8 amplitudes a
-// thread owns.  Only the non-empty classes are listed: nibble k of `ids` is the class of the
+// w = (z >> CLASS_SHIFT) & CLASS_MASK, i.e. by the z bits that distinguish the 2^CLASS_BITS
+// amplitudes a thread owns (at most SEG_MAX_RUNS class runs per segment).  Only the non-empty classes are listed: nibble k of `ids` is the class of the
 // k-th run of terms and byte k of `cnts` its length.
 #ifndef OFB_APPLY_BLOCK_BITS
-#define OFB_APPLY_BLOCK_BITS 7
+#define OFB_APPLY_BLOCK_BITS 6
 #endif
-#ifndef OFB_APPLY_MIN_CTAS
-#define OFB_APPLY_MIN_CTAS 4
+#ifndef OFB_APPLY_CLASS_BITS
+#define OFB_APPLY_CLASS_BITS 4  // a thread owns 2^CLASS_BITS amplitudes (3 or 4)
+#endif
+#ifndef OFB_APPLY_MIN_CTAS  // 64-thread CTAs: 6 per SM at 167 registers (16 amplitudes), 8 at 113 (8)
+#define OFB_APPLY_MIN_CTAS (OFB_APPLY_CLASS_BITS == 3 ? 8 : 6)
 #endif
 constexpr int CLASS_SHIFT = OFB_APPLY_BLOCK_BITS;  // log2(threads per block) of the apply kernel
+constexpr int CLASS_BITS = OFB_APPLY_CLASS_BITS;
+constexpr uint32_t CLASS_MASK = (1u << CLASS_BITS) - 1u;
+constexpr int SEG_MAX_RUNS = 8;  // nibbles of Segment::ids / bytes of Segment::cnts
+static_assert(CLASS_BITS == 3 || CLASS_BITS == 4, "class ids are stored in nibbles");
 constexpr int SEG_MAX_TERMS = 255;
 struct __align__(16) Segment {
     uint32_t x_lo;       // low 32 bits of the x mask (all a device-local index can use)

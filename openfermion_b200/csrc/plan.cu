@@ -339,12 +339,28 @@ int ofb_plan_create(int n_qubits, int64_t n_terms, const uint64_t *x_mask, const
         p->h_seg_begin[g] = (uint32_t)segs.size();
         idx.resize(e - b);
         std::iota(idx.begin(), idx.end(), b);
-        auto cls_of = [&](uint32_t k) { return (uint32_t)(z_mask[order[k]] >> CLASS_SHIFT) & 7u; };
+        auto cls_of = [&](uint32_t k) { return (uint32_t)(z_mask[order[k]] >> CLASS_SHIFT) & CLASS_MASK; };
         std::stable_sort(idx.begin(), idx.end(),
                          [&](uint32_t a, uint32_t c2) { return cls_of(a) < cls_of(c2); });
-        for (size_t pos = 0; pos < idx.size(); pos += SEG_MAX_TERMS) {
+        for (size_t pos = 0; pos < idx.size();) {
             size_t end = std::min(idx.size(), pos + (size_t)SEG_MAX_TERMS);
-            // a chunk of a class-sorted list is still class-sorted
+            // a chunk of a class-sorted list is still class-sorted; a segment also ends before
+            // its (SEG_MAX_RUNS + 1)-th class run (only possible with 16 classes)
+            {
+                uint32_t seen = 0;
+                int prev = -1;
+                for (size_t q = pos; q < end; ++q) {
+                    int cw = (int)cls_of(idx[q]);
+                    if (cw != prev) {
+                        if (seen == (uint32_t)SEG_MAX_RUNS) {
+                            end = q;
+                            break;
+                        }
+                        ++seen;
+                        prev = cw;
+                    }
+                }
+            }
             Segment sd{};
             sd.x = p->h_group_x[g];
             sd.x_lo = (uint32_t)p->h_group_x[g];
@@ -368,6 +384,7 @@ int ofb_plan_create(int n_qubits, int64_t n_terms, const uint64_t *x_mask, const
             sd.cnts = cnts;
             sd.ids = ids;
             segs.push_back(sd);
+            pos = end;
         }
     }
     p->h_seg_begin[p->n_groups] = (uint32_t)segs.size();

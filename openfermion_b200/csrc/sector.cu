@@ -143,8 +143,11 @@ __device__ __forceinline__ int64_t sector_pos_fast(const SectorDev &s, uint64_t 
         return -1;
     }
     if (POS32 && s.n_classes == 1) {
-        const uint32_t v = (uint32_t)jx;
-        return (int64_t)(uint32_t)(s.A32[v >> s.lo_bits] + s.B[v & (uint32_t)s.lo_mask]);
+        if (Z32) {
+            const uint32_t v = (uint32_t)jx;
+            return (int64_t)(uint32_t)(s.A32[v >> s.lo_bits] + s.B[v & (uint32_t)s.lo_mask]);
+        }
+        return (int64_t)(uint32_t)(s.A32[jx >> s.lo_bits] + s.B[jx & s.lo_mask]);
     }
     return sector_table_pos(s, jx);
 }
