@@ -43,27 +43,38 @@ __device__ __forceinline__ uint32_t sign_parity(uint64_t z, uint32_t j_lo, uint3
 
 // sigma-signed sum of `cnt` consecutive table entries (one class run).  The sign is folded
 // into the high word with one add: hi + (parity << 31) flips bit 31 (mod 2^32).  Two entries
-// per iteration on independent accumulators; the loads of the next pair are issued before the
-// current pair is consumed, so the shared-memory latency overlaps the popc/add chains.
+// per iteration on independent accumulators, software pipelined: the caller passes the first
+// pair already loaded (`e0`, `e1`, issued before the previous run's FMAs) and every iteration
+// issues the loads of the next pair before consuming the current one, so the shared-memory
+// latency overlaps the popc/add chains even at three warps per scheduler.  Reads may run up to
+// two entries past the run (the staging buffers are padded); those values are never used.
 template <bool Z32>
-__device__ __forceinline__ double run_sum(const TermZC *tab, uint32_t cnt, uint32_t j_lo,
-                                          uint32_t base_hi) {
+__device__ __forceinline__ double signed_entry(const TermZC &e, uint32_t j_lo, uint32_t base_hi) {
+    return __hiloint2double(__double2hiint(e.c) + (int)(sign_parity<Z32>(e.z, j_lo, base_hi) << 31),
+                            __double2loint(e.c));
+}
+
+template <bool Z32>
+__device__ __forceinline__ double run_sum(const TermZC *tab, uint32_t cnt, TermZC e0, TermZC e1,
+                                          uint32_t j_lo, uint32_t base_hi) {
     double a0 = 0.0, a1 = 0.0;
-    const TermZC *p = tab;
+    const TermZC *p = tab + 2;
     const TermZC *end2 = tab + (cnt & ~1u);
+    if (cnt >= 2u) {
 #pragma unroll 1
-    while (p != end2) {
-        const TermZC e0 = p[0], e1 = p[1];
-        p += 2;
-        a0 += __hiloint2double(__double2hiint(e0.c) + (int)(sign_parity<Z32>(e0.z, j_lo, base_hi) << 31),
-                               __double2loint(e0.c));
-        a1 += __hiloint2double(__double2hiint(e1.c) + (int)(sign_parity<Z32>(e1.z, j_lo, base_hi) << 31),
-                               __double2loint(e1.c));
-    }
-    if (cnt & 1u) {
-        const TermZC e0 = p[0];
-        a0 += __hiloint2double(__double2hiint(e0.c) + (int)(sign_parity<Z32>(e0.z, j_lo, base_hi) << 31),
-                               __double2loint(e0.c));
+        while (p != end2) {
+            const TermZC n0 = p[0], n1 = p[1];
+            p += 2;
+            a0 += signed_entry<Z32>(e0, j_lo, base_hi);
+            a1 += signed_entry<Z32>(e1, j_lo, base_hi);
+            e0 = n0;
+            e1 = n1;
+        }
+        a0 += signed_entry<Z32>(e0, j_lo, base_hi);
+        a1 += signed_entry<Z32>(e1, j_lo, base_hi);
+        if (cnt & 1u) a0 += signed_entry<Z32>(end2[0], j_lo, base_hi);
+    } else {  // cnt == 1: the preloaded first entry is the whole run
+        a0 = signed_entry<Z32>(e0, j_lo, base_hi);
     }
     return a0 + a1;
 }
@@ -120,17 +131,21 @@ __device__ __forceinline__ void segment_pass(const TermZC *tab, uint32_t runs, u
                                              uint32_t ids, uint32_t j_lo, uint32_t base_hi,
                                              const double2 (&v)[R8], double (&ar)[R8],
                                              double (&ai)[R8]) {
+    TermZC e0 = tab[0], e1 = tab[1];
     if (runs == 1) {  // the common case: no run bookkeeping at all
-        const double a = run_sum<Z32>(tab, (uint32_t)cnts, j_lo, base_hi);
+        const double a = run_sum<Z32>(tab, (uint32_t)cnts, e0, e1, j_lo, base_hi);
         apply_class_dyn<IMAG>(ids, a, v, ar, ai);
         return;
     }
 #pragma unroll 1
     for (uint32_t k = 0; k < runs; ++k) {
         const uint32_t cnt = (uint32_t)cnts & 0xffu;
-        const double a = run_sum<Z32>(tab, cnt, j_lo, base_hi);
-        apply_class_dyn<IMAG>(ids & 0xfu, a, v, ar, ai);
+        const double a = run_sum<Z32>(tab, cnt, e0, e1, j_lo, base_hi);
         tab += cnt;
+        // first pair of the next run: in flight while this run's FMAs execute
+        e0 = tab[0];
+        e1 = tab[1];
+        apply_class_dyn<IMAG>(ids & 0xfu, a, v, ar, ai);
         cnts >>= 8;
         ids >>= 4;
     }
