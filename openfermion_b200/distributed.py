@@ -145,6 +145,9 @@ class ShardedPauliOperator:
         want = n_remote if max_staging is None else min(max_staging, n_remote)
         self._staging = [self._new() for _ in range(want)] if mode in ('nccl', 'ce') else []
         self._copy_stream = None
+        self._copy_lanes = max(1, int(os.environ.get('OFB_CE_LANES', '1')))
+        while self._copy_lanes > 1 and (self.dim * 16) % (self._copy_lanes * 256):
+            self._copy_lanes //= 2
         self._events = []
         self._peer_vectors = {}  # p2p: vector id -> list of per-rank device pointers
         self._opened = []
@@ -224,32 +227,43 @@ class ShardedPauliOperator:
         ptrs = self._peer_vectors.get(vin.ptr)
         if ptrs is None:
             raise RuntimeError('ce mode: vector was not registered with register_peer_vectors')
+        depth = len(self._staging)
+        lanes = self._copy_lanes
         if self._copy_stream is None:
-            s = vp()
-            lib.call('ofb_stream_create', ctypes.byref(s))
-            self._copy_stream = s
-            for _ in range(2 * max(len(self._staging), 1) + 1):
+            # a shard copy can be cut into OFB_CE_LANES pieces on as many streams (several copy
+            # engines pulling at once).  Measured on 8 B200s: 4 lanes 88.8 ms per step against
+            # 72.7 ms with one lane -- the concurrent copies take HBM bandwidth from the
+            # kernels they are meant to hide behind -- so the default is one lane.
+            self._copy_stream = []
+            for _ in range(lanes):
+                s = vp()
+                lib.call('ofb_stream_create', ctypes.byref(s))
+                self._copy_stream.append(s)
+            for _ in range((lanes + 1) * max(depth, 1) + 1):
                 e = vp()
                 lib.call('ofb_event_create', ctypes.byref(e))
                 self._events.append(e)
-        depth = len(self._staging)
         main = vp(self._stream())
-        copied = self._events[:depth]            # copy i landed in staging[i % depth]
-        consumed = self._events[depth:2 * depth]  # kernel finished reading staging[i % depth]
-        start = self._events[2 * depth]
-        nbytes = ctypes.c_size_t(self.dim * 16)
+        # copied[slot][lane]: piece `lane` of the copy into staging[slot] landed
+        copied = [self._events[k * lanes:(k + 1) * lanes] for k in range(depth)]
+        consumed = self._events[depth * lanes:depth * lanes + depth]  # kernel done with staging[slot]
+        start = self._events[depth * lanes + depth]
+        piece = self.dim * 16 // lanes
         # copies may start once everything already queued on the main stream (the previous
         # step's kernels, which read the staging buffers) is done
         lib.call('ofb_event_record', start, main)
-        lib.call('ofb_stream_wait_event', self._copy_stream, start)
+        for stream in self._copy_stream:
+            lib.call('ofb_stream_wait_event', stream, start)
 
         def post(i):
             peer = layout.peer(self.rank, remote[i][0])
-            if i >= depth:
-                lib.call('ofb_stream_wait_event', self._copy_stream, consumed[i % depth])
-            lib.call('ofb_memcpy_d2d', vp(self._staging[i % depth].ptr), vp(ptrs[peer]), nbytes,
-                     self._copy_stream)
-            lib.call('ofb_event_record', copied[i % depth], self._copy_stream)
+            slot = i % depth
+            for lane, stream in enumerate(self._copy_stream):
+                if i >= depth:
+                    lib.call('ofb_stream_wait_event', stream, consumed[slot])
+                lib.call('ofb_memcpy_d2d', vp(self._staging[slot].ptr + lane * piece),
+                         vp(ptrs[peer] + lane * piece), ctypes.c_size_t(piece), stream)
+                lib.call('ofb_event_record', copied[slot][lane], stream)
 
         for i in range(min(depth, len(remote))):
             post(i)
@@ -259,7 +273,8 @@ class ShardedPauliOperator:
             self._local_apply(vin, vout, g0, g1, False)
             first = False
         for i, (x_hi, g0, g1) in enumerate(remote):
-            lib.call('ofb_stream_wait_event', main, copied[i % depth])
+            for event in copied[i % depth]:
+                lib.call('ofb_stream_wait_event', main, event)
             self._local_apply(self._staging[i % depth], vout, g0, g1, not first)
             first = False
             lib.call('ofb_event_record', consumed[i % depth], main)
