@@ -376,6 +376,8 @@ def main():
                     help='state size of the bounded sample of the --impl reference arm')
     ap.add_argument('--dist-qubits', type=int, default=32, help='N>1 workload size (Hubbard)')
     ap.add_argument('--dist-mode', default='ce', choices=['ce', 'nccl', 'p2p'])
+    ap.add_argument('--dist-basis', default='symmetry', choices=['symmetry', 'natural'],
+                    help='N>1: shard by conserved parities first (no exchange for them) or by the top qubits')
     ap.add_argument('--dist-diagnose', action='store_true')
     args = ap.parse_args()
     if args.impl == 'reference':

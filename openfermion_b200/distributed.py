@@ -36,6 +36,7 @@ import numpy
 
 from openfermion_b200.compiler import compile_qubit_operator
 from openfermion_b200.ops import count_qubits
+from openfermion_b200.shard_basis import ShardBasis
 
 
 # ----------------------------------------------------------------------------
@@ -109,7 +110,8 @@ class ShardedPauliOperator:
     """
 
     def __init__(self, operator, n_qubits=None, dist=None, group=None, mode='nccl',
-                 max_staging=None, local_apply=None, vector_factory=None, tensor_of=None):
+                 max_staging=None, local_apply=None, vector_factory=None, tensor_of=None,
+                 basis='natural'):
         self.dist = dist
         self.group = group
         self.rank = dist.get_rank(group) if dist is not None else 0
@@ -120,6 +122,22 @@ class ShardedPauliOperator:
         if self.n_qubits < needed:
             raise ValueError('Invalid number of qubits specified.')
         x, z, c = compile_qubit_operator(operator, self.n_qubits)
+        # basis: 'natural' = shard by the top qubits; 'symmetry' = shard by conserved parities
+        # first (shard_basis.py), which removes peer exchanges; or a ShardBasis instance.
+        # Shards then hold psi'[c'] = psi[B^-1 c']: see shard_of / natural_indices.
+        shard_bits = max(self.world, 1).bit_length() - 1
+        if basis == 'natural':
+            basis = ShardBasis.natural(self.n_qubits)
+        elif basis == 'symmetry':
+            basis = ShardBasis.for_sharding(self.n_qubits, min(shard_bits, self.n_qubits), x)
+        elif not isinstance(basis, ShardBasis):
+            raise ValueError("basis must be 'natural', 'symmetry' or a ShardBasis")
+        if basis.n_qubits != self.n_qubits:
+            raise ValueError('shard basis is for {} qubits, operator has {}'.format(
+                basis.n_qubits, self.n_qubits))
+        self.basis = basis
+        self._natural_x = x
+        x, z, c = basis.transform_terms(x, z, c)
         self.layout = ShardLayout(self.n_qubits, self.world, x)
         self.n_terms = len(c)
         self.n_groups = len(self.layout.group_x)
@@ -182,6 +200,19 @@ class ShardedPauliOperator:
 
     def new_vector(self):
         return self._new()
+
+    def natural_indices(self, rank=None):
+        """Natural (reference-order) index of every amplitude of a rank's shard."""
+        rank = self.rank if rank is None else rank
+        return self.basis.shard_natural_indices(rank, self.layout.local_bits)
+
+    def shard_of(self, full_state, rank=None):
+        """This rank's shard of a full-length host vector given in the reference's order."""
+        full_state = numpy.asarray(full_state)
+        if self.basis.identity:
+            rank = self.rank if rank is None else rank
+            return full_state[rank * self.dim:(rank + 1) * self.dim].copy()
+        return full_state[self.natural_indices(rank).astype(numpy.int64)]
 
     # -- p2p registration ------------------------------------------------------------------
     def register_peer_vectors(self, vectors):
@@ -438,20 +469,23 @@ def bench_main(args, metric, unit, clock_sampler_cls, measured_peak):
         dims = {12: (2, 3), 16: (2, 4), 20: (2, 5), 24: (3, 4), 28: (2, 7), 30: (3, 5)}[sites * 2]
         op_model, name = hamiltonians.hubbard_jw(*dims), 'Fermi-Hubbard %dx%d spinful JW, %d qubits' % (dims + (n,))
     mode = args.dist_mode
-    op = ShardedPauliOperator(op_model, n, dist=dist, mode=mode)
+    op = ShardedPauliOperator(op_model, n, dist=dist, mode=mode,
+                              basis=getattr(args, 'dist_basis', 'symmetry'))
     layout = op.layout
+    natural_layout = ShardLayout(n, world, op._natural_x)
     dim_local = op.dim
     vin, vout = op.new_vector(), op.new_vector()
     krylov.fill_random(dim_local, 42 + rank, False, vin.ptr)
     comm = TorchComm(dist, 'cuda:%d' % local_rank)
     krylov.scal(dim_local, 1.0 / krylov.gnorm(dim_local, vin.ptr, comm), vin.ptr)
-    if mode in ('p2p', 'ce'):
+    exchanging = mode in ('p2p', 'ce') and bool(layout.remote_patterns)
+    if exchanging:
         op.register_peer_vectors([vin])
     T, G = op.n_terms, op.n_groups
     start, stop = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
 
     def step():
-        if mode in ('p2p', 'ce'):
+        if exchanging:
             comm.barrier()  # peers must have finished writing the vector we are about to read
         op.matvec(vin, vout)
 
@@ -547,8 +581,10 @@ def bench_main(args, metric, unit, clock_sampler_cls, measured_peak):
             'warmup': args.warmup, 'ms_per_step': ms / args.steps, 'higher_is_better': True,
             'scaling': 'strong', 'vs_baseline': None, 'dtype': 'f64', 'data': 'synthetic',
             'config': {'workload': name, 'n_qubits': n, 'terms': T, 'x_groups': G,
-                       'sharding': 'top %d qubits over %d ranks' % (layout.shard_bits, world),
+                       'sharding': '%d shard bits over %d ranks: %s' % (
+                           layout.shard_bits, world, op.basis.describe(layout.shard_bits)),
                        'exchange': mode, 'remote_patterns': len(layout.remote_patterns),
+                       'remote_patterns_top_qubit_sharding': len(natural_layout.remote_patterns),
                        'exchange_bytes_per_rank_per_step': layout.exchange_bytes_per_matvec() if mode in ('nccl', 'ce') else None,
                        'l2_policy': 'inputs exceed L2 (%.1f GB per shard)' % (dim_local * 16 / 1e9),
                        'timing': 'CUDA events, max over ranks', 'expectation_check': [e.real, e.imag],

@@ -23,6 +23,7 @@ def main():
     ap.add_argument('--x', type=int, default=4)
     ap.add_argument('--y', type=int, default=4)
     ap.add_argument('--mode', default='ce')
+    ap.add_argument('--basis', default='symmetry', choices=['symmetry', 'natural'])
     ap.add_argument('--tol', type=float, default=1e-8)
     ap.add_argument('--krylov', type=int, default=120)
     args = ap.parse_args()
@@ -31,7 +32,7 @@ def main():
     dist = init_nccl(local)
     _lib.call('ofb_set_device', ctypes.c_int(local))
     op = hamiltonians.hubbard_jw(args.x, args.y)
-    sop = ShardedPauliOperator(op, op.n_qubits, dist=dist, mode=args.mode)
+    sop = ShardedPauliOperator(op, op.n_qubits, dist=dist, mode=args.mode, basis=args.basis)
     stats = {}
     import torch
     torch.cuda.synchronize()
@@ -43,7 +44,9 @@ def main():
     dt = time.perf_counter() - t0
     if rank == 0:
         print(json.dumps({'config': 'Fermi-Hubbard %dx%d (%d qubits) sharded Lanczos' % (args.x, args.y, op.n_qubits),
-                          'n_gpus': world, 'exchange': args.mode, 'E0': energy, 'residual': residual,
+                          'n_gpus': world, 'exchange': args.mode,
+                          'shard_bits': sop.basis.describe(sop.layout.shard_bits),
+                          'peer_shards_per_matvec': len(sop.layout.remote_patterns), 'E0': energy, 'residual': residual,
                           'matvecs': stats.get('matvecs'), 'restarts': stats.get('restarts'),
                           'seconds': dt, 'seconds_per_matvec_incl_vector_ops': dt / max(stats.get('matvecs', 1), 1)}))
     sop.close()

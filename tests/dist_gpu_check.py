@@ -30,11 +30,13 @@ def main():
                         ('dense_complex_14', hamiltonians.random_pauli_sum(14, 300, 3, True), 14)):
         rng = numpy.random.default_rng(1)
         full = rng.normal(size=1 << n) + 1j * rng.normal(size=1 << n)
-        for mode in ('nccl', 'p2p', 'ce'):
-            sop = ShardedPauliOperator(op, n, dist=dist, mode=mode, max_staging=1 if mode in ('nccl', 'ce') else None)
+        for mode, basis in (('nccl', 'natural'), ('p2p', 'natural'), ('ce', 'natural'),
+                            ('ce', 'symmetry'), ('nccl', 'symmetry'), ('p2p', 'symmetry')):
+            sop = ShardedPauliOperator(op, n, dist=dist, mode=mode, basis=basis,
+                                       max_staging=1 if mode in ('nccl', 'ce') else None)
             ld = sop.dim
             vin, vout = sop.new_vector(), sop.new_vector()
-            krylov.upload(full[rank * ld:(rank + 1) * ld], vin.ptr)
+            krylov.upload(numpy.ascontiguousarray(sop.shard_of(full)), vin.ptr)
             if mode in ('p2p', 'ce'):
                 sop.register_peer_vectors([vin])
                 TorchComm(dist, 'cuda:%d' % local).barrier()
@@ -45,8 +47,10 @@ def main():
             dist.all_gather_object(gathered, got)
             if rank == 0:
                 want = LinearQubitOperator(op, n) * full
-                err = numpy.max(numpy.abs(numpy.concatenate(gathered) - want)) / numpy.max(numpy.abs(want))
-                print('%s %s world=%d rel_err=%.2e patterns=%d' % (name, mode, world, err, len(sop.layout.remote_patterns)))
+                result = sop.basis.to_natural(numpy.concatenate(gathered))
+                err = numpy.max(numpy.abs(result - want)) / numpy.max(numpy.abs(want))
+                print('%s %s basis=%s world=%d rel_err=%.2e patterns=%d' % (
+                    name, mode, basis, world, err, len(sop.layout.remote_patterns)))
                 ok = ok and err < 1e-12
             dist.barrier()
             sop.close()
@@ -54,13 +58,13 @@ def main():
     e1 = None
     if rank == 0:
         e1, _ = get_ground_state(LinearQubitOperator(hub, 16))
-    for mode in ('nccl', 'ce'):
-        sop = ShardedPauliOperator(hub, 16, dist=dist, mode=mode)
+    for mode, basis in (('nccl', 'natural'), ('ce', 'natural'), ('ce', 'symmetry')):
+        sop = ShardedPauliOperator(hub, 16, dist=dist, mode=mode, basis=basis)
         stats = {}
         energy, _, residual = lanczos_ground_state(sop, dist, stats=stats)
         if rank == 0:
-            print('lanczos %s world=%d E=%.12f single-GPU E=%.12f diff=%.2e residual=%.2e matvecs=%d'
-                  % (mode, world, energy, e1, abs(energy - e1), residual, stats.get('matvecs', 0)))
+            print('lanczos %s/%s world=%d E=%.12f single-GPU E=%.12f diff=%.2e residual=%.2e matvecs=%d'
+                  % (mode, basis, world, energy, e1, abs(energy - e1), residual, stats.get('matvecs', 0)))
             ok = ok and abs(energy - e1) < 1e-10
         sop.close()
     if rank == 0:

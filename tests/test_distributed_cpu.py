@@ -41,22 +41,21 @@ def _make_operator(kind):
     return op, 6
 
 
-def _worker(rank, world, port, kind, depth, out_dir):
+def _worker(rank, world, port, kind, depth, out_dir, basis='natural'):
     os.environ['MASTER_ADDR'] = '127.0.0.1'
     os.environ['MASTER_PORT'] = str(port)
     dist.init_process_group('gloo', rank=rank, world_size=world)
     try:
         operator, n = _make_operator(kind)
-        from openfermion_b200.compiler import compile_qubit_operator
-        x, z, c = compile_qubit_operator(operator, n)
-        layout = ShardLayout(n, world, x)
-        ld = layout.local_dim
-        j = numpy.arange(ld, dtype=numpy.uint64)
-        jg = j | numpy.uint64(rank << layout.local_bits)
-        group_of = numpy.searchsorted(layout.group_x, x)
         applied = []
+        ctx = {}
 
         def local_apply(vin, vout, g0, g1, accumulate):
+            # numpy restatement of the gather form on this rank's shard, over the operator's
+            # own (possibly relabelled) tables
+            x, z, c = ctx['tables']
+            layout, j, jg, group_of = ctx['layout'], ctx['j'], ctx['jg'], ctx['group_of']
+            ld = layout.local_dim
             applied.append((g0, g1, accumulate))
             out = vout.array
             if not accumulate:
@@ -71,14 +70,19 @@ def _worker(rank, world, port, kind, depth, out_dir):
 
         op = ShardedPauliOperator(
             operator, n, dist=dist, mode='nccl', max_staging=depth, local_apply=local_apply,
-            vector_factory=lambda: _HostVec(ld),
-            tensor_of=lambda v: torch.from_numpy(v.array.view(numpy.float64)))
+            vector_factory=lambda: _HostVec(1 << (n - (world.bit_length() - 1))),
+            tensor_of=lambda v: torch.from_numpy(v.array.view(numpy.float64)), basis=basis)
+        layout = op.layout
+        ld = layout.local_dim
+        j = numpy.arange(ld, dtype=numpy.uint64)
+        ctx.update(tables=op._tables, layout=layout, j=j, jg=j | numpy.uint64(rank << layout.local_bits),
+                   group_of=numpy.searchsorted(layout.group_x, op._tables[0]))
         rng = numpy.random.default_rng(3)
         full = rng.normal(size=1 << n) + 1j * rng.normal(size=1 << n)
         vin, vout = op.new_vector(), op.new_vector()
-        vin.array[:] = full[rank * ld:(rank + 1) * ld]
+        vin.array[:] = op.shard_of(full)
         op.matvec(vin, vout)
-        want = po.matvec(operator.terms, n, full)[rank * ld:(rank + 1) * ld]
+        want = op.shard_of(po.matvec(operator.terms, n, full))
         err = float(numpy.max(numpy.abs(vout.array - want)))
         # every group applied exactly once, first call overwrites, later calls accumulate
         covered = sorted((a, b) for a, b, _ in applied if b > a)
@@ -87,9 +91,13 @@ def _worker(rank, world, port, kind, depth, out_dir):
         comm = TorchComm(dist, 'cpu')
         total = comm.allsum(numpy.vdot(vin.array, vout.array))
         want_total = numpy.vdot(full, po.matvec(operator.terms, n, full))
+        # the shards of all ranks tile the natural index space exactly once
+        seen = numpy.zeros(1 << n, dtype=numpy.int64)
+        for r in range(world):
+            seen[op.natural_indices(r).astype(numpy.int64)] += 1
         numpy.save(os.path.join(out_dir, 'r%d.npy' % rank),
                    numpy.array([err, float(ok_cover), float(ok_flags), abs(total - want_total),
-                                len(layout.remote_patterns)]))
+                                len(layout.remote_patterns), float(numpy.all(seen == 1))]))
     finally:
         dist.destroy_process_group()
 
@@ -101,10 +109,27 @@ def test_sharded_matvec_over_gloo(world, kind, depth, tmp_path):
     mp.start_processes(_worker, args=(world, port, kind, depth, str(tmp_path)), nprocs=world,
                        join=True, start_method='fork')
     for rank in range(world):
-        err, ok_cover, ok_flags, dot_err, n_remote = numpy.load(tmp_path / ('r%d.npy' % rank))
+        err, ok_cover, ok_flags, dot_err, n_remote, tiled = numpy.load(tmp_path / ('r%d.npy' % rank))
         assert err < 1e-12, (rank, err)
-        assert ok_cover == 1.0 and ok_flags == 1.0
+        assert ok_cover == 1.0 and ok_flags == 1.0 and tiled == 1.0
         assert dot_err < 1e-11
+
+
+@pytest.mark.parametrize('world,kind,remote', [(2, 'hubbard', 0), (4, 'hubbard', 0), (8, 'hubbard', 1),
+                                               (4, 'complex', None), (2, 'small', 0)])
+def test_symmetry_basis_sharded_matvec_over_gloo(world, kind, remote, tmp_path):
+    """Sharding by conserved parities (shard_basis.py): same H|psi> after relabelling, and the
+    spin-parity bits of a Hubbard model need no peer shard at all."""
+    port = _free_port()
+    mp.start_processes(_worker, args=(world, port, kind, None, str(tmp_path), 'symmetry'), nprocs=world,
+                       join=True, start_method='fork')
+    for rank in range(world):
+        err, ok_cover, ok_flags, dot_err, n_remote, tiled = numpy.load(tmp_path / ('r%d.npy' % rank))
+        assert err < 1e-12, (rank, err)
+        assert ok_cover == 1.0 and ok_flags == 1.0 and tiled == 1.0
+        assert dot_err < 1e-11
+        if remote is not None:
+            assert n_remote == remote
 
 
 def test_shard_layout_patterns():

@@ -341,25 +341,37 @@ def test_csc_fermion_route_equals_pauli_route_spectrum():
 
 
 # ---- sharded kernel form on one GPU (virtual ranks) -------------------------------------------
+@pytest.mark.parametrize('basis_kind', ['natural', 'symmetry'])
 @pytest.mark.parametrize('builder,n,world', [(lambda: hamiltonians.hubbard_jw(2, 4), 16, 4),
+                                             (lambda: hamiltonians.hubbard_jw(2, 4), 16, 8),
                                              (lambda: hamiltonians.molecular_jw(6, seed=1234), 12, 8),
+                                             (lambda: hamiltonians.molecular_jw(5, seed=3, encoding='bk'), 10, 4),
                                              (lambda: hamiltonians.random_pauli_sum(13, 200, 2, True), 13, 2)])
-def test_virtual_rank_sharding_matches_unsharded(builder, n, world):
+def test_virtual_rank_sharding_matches_unsharded(builder, n, world, basis_kind):
     """Every rank's shard is another region of one device buffer (the p2p data path with
     pointers into the same GPU): ofb_apply_groups with local_bits < n, a per-rank index_base,
-    per-pattern group ranges and accumulate must reproduce the unsharded H|psi>."""
+    per-pattern group ranges and accumulate must reproduce the unsharded H|psi> -- with the
+    shards cut by the top qubits and by conserved parities (shard_basis.py: relabelled masks,
+    relabelled state, same kernel)."""
     from openfermion_b200 import _lib
     from openfermion_b200.distributed import ShardLayout
     from openfermion_b200.linalg import krylov
+    from openfermion_b200.plan import PauliPlan
+    from openfermion_b200.shard_basis import ShardBasis
     op = builder()
     lin = LinearQubitOperator(op, n)
-    plan = lin.plan
-    x, _, _ = compiler.compile_qubit_operator(op, n)
+    x, z, c = compiler.compile_qubit_operator(op, n)
+    if basis_kind == 'natural':
+        basis, plan = ShardBasis.natural(n), lin.plan
+    else:
+        basis = ShardBasis.for_sharding(n, world.bit_length() - 1, x)
+        x, z, c = basis.transform_terms(x, z, c)
+        plan = PauliPlan(n, x, z, c)
     layout = ShardLayout(n, world, x)
     assert numpy.array_equal(layout.group_x, plan.group_x_masks())
     v = _state(n, 11)
     want = lin * v
-    d_in = _lib.to_device(v)
+    d_in = _lib.to_device(basis.from_natural(v))
     d_out = _lib.DeviceBuffer(v.nbytes)
     ld = layout.local_dim
     for rank in range(world):
@@ -369,7 +381,7 @@ def test_virtual_rank_sharding_matches_unsharded(builder, n, world):
             plan.apply_groups_device(src, d_out.ptr + rank * ld * 16, layout.local_bits,
                                      layout.index_base(rank), g0, g1, 0 if first else 1)
             first = False
-    got = krylov.download(1 << n, d_out.ptr)
+    got = basis.to_natural(krylov.download(1 << n, d_out.ptr))
     assert helpers.close(got, want, 1e-13)
 
 
