@@ -6,6 +6,7 @@ Materialisation runs the count/scan/fill CSC kernels (K4), the diagonal runs K3,
 expectation runs the fused K2 kernel and get_ground_state / get_gap run the
 device-resident Lanczos loop on top of K1.
 """
+import functools
 import itertools
 
 import numpy
@@ -45,6 +46,30 @@ def jordan_wigner_sparse(fermion_operator, n_qubits=None):
         return plan.csc_host()
     finally:
         plan.close()
+
+
+def jordan_wigner_ladder_sparse(n_qubits, tensor_factor, ladder_type):
+    """CSC matrix of one ladder operator, a_j^dagger (ladder_type truthy) or a_j on mode
+    `tensor_factor` (sparse_tools.py:49-73: Z_0..Z_{j-1} (X_j -/+ iY_j)/2).  The reference
+    chains Kronecker products of 2x2 blocks; here it is the one-factor case of the fermion
+    route, built by the CSC kernels (K4)."""
+    if not 0 <= tensor_factor < n_qubits:
+        raise ValueError('tensor_factor must address one of the n_qubits modes.')
+    operator = ops.FermionOperator(((int(tensor_factor), 1 if ladder_type else 0),), 1.0)
+    return jordan_wigner_sparse(operator, n_qubits)
+
+
+def wrapped_kronecker(operator_1, operator_2):
+    """Kronecker product of two sparse matrices as CSC (sparse_tools.py:39-41).  A generic
+    scipy helper of the reference, kept for callers that assemble their own operators; the
+    Hamiltonian builders above never form Kronecker chains."""
+    return scipy.sparse.kron(operator_1, operator_2, 'csc')
+
+
+def kronecker_operators(*args):
+    """Kronecker product of a list of sparse matrices (sparse_tools.py:44-46); like the
+    reference it takes the list as its single positional argument."""
+    return functools.reduce(wrapped_kronecker, *args)
 
 
 def _tensor_fermion_terms(operator):

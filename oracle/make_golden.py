@@ -345,9 +345,43 @@ def operator_file_cases():
     print('operator files written')
 
 
+def ladder_cases():
+    """Single ladder-operator matrices of the reference (sparse_tools.py:49-73) and the
+    Kronecker helpers they are built with (:39-46)."""
+    from openfermion.linalg import jordan_wigner_ladder_sparse, kronecker_operators, wrapped_kronecker
+    cases = {}
+    names = []
+    for n, mode, kind in ((1, 0, 1), (1, 0, 0), (3, 0, 1), (3, 2, 0), (5, 2, 1), (6, 5, 0), (9, 4, 1), (11, 0, 0)):
+        ref = jordan_wigner_ladder_sparse(n, mode, kind)
+        assert same_csc(ref, po.jordan_wigner_sparse({((mode, kind),): 1.0}, n)), (n, mode, kind)
+        name = 'n%d_m%d_%s' % (n, mode, 'raise' if kind else 'lower')
+        cases[name + '/args'] = numpy.array([n, mode, kind])
+        cases[name + '/indptr'] = ref.indptr
+        cases[name + '/indices'] = ref.indices
+        cases[name + '/data'] = ref.data
+        cases[name + '/index_dtype'] = numpy.array(str(ref.indices.dtype))
+        names.append(name)
+    rng = numpy.random.default_rng(11)
+    a = scipy.sparse.random(3, 4, 0.5, format='csc', random_state=rng, dtype=float) * (1 + 0.5j)
+    b = scipy.sparse.random(2, 2, 0.8, format='csc', random_state=rng, dtype=float)
+    c = scipy.sparse.identity(3, dtype=complex, format='csc')
+    for tag, mat in (('ab', wrapped_kronecker(a, b)), ('abc', kronecker_operators([a, b, c]))):
+        cases['kron_' + tag + '/indptr'] = mat.indptr
+        cases['kron_' + tag + '/indices'] = mat.indices
+        cases['kron_' + tag + '/data'] = mat.data
+        cases['kron_' + tag + '/shape'] = numpy.array(mat.shape)
+    for tag, mat in (('a', a), ('b', b), ('c', c)):
+        cases['kron_in_' + tag] = mat.toarray()
+    cases['names'] = numpy.array(names, dtype=str)
+    numpy.savez_compressed(os.path.join(GOLDEN, 'ladder_cases.npz'), **cases)
+    print('ladder_cases:', len(names), 'cases')
+
+
 if __name__ == '__main__':
     os.makedirs(GOLDEN, exist_ok=True)
-    which = sys.argv[1:] or ['qubit', 'fermion', 'lih', 'sector', 'files']
+    which = sys.argv[1:] or ['qubit', 'fermion', 'lih', 'sector', 'files', 'ladder']
+    if 'ladder' in which:
+        ladder_cases()
     if 'qubit' in which:
         qubit_cases()
     if 'fermion' in which:

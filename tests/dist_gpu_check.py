@@ -25,13 +25,17 @@ def main():
     init_nccl(local)
     _lib.call('ofb_set_device', ctypes.c_int(local))
     ok = True
+    quick = bool(os.environ.get('OFB_DIST_QUICK'))  # fewer mode/basis combinations (GPU-minutes)
     for name, op, n in (('hubbard_2x4', hamiltonians.hubbard_jw(2, 4), 16),
                         ('molecular_12', hamiltonians.molecular_jw(6, seed=1234), 12),
                         ('dense_complex_14', hamiltonians.random_pauli_sum(14, 300, 3, True), 14)):
         rng = numpy.random.default_rng(1)
         full = rng.normal(size=1 << n) + 1j * rng.normal(size=1 << n)
-        for mode, basis in (('nccl', 'natural'), ('p2p', 'natural'), ('ce', 'natural'),
-                            ('ce', 'symmetry'), ('nccl', 'symmetry'), ('p2p', 'symmetry')):
+        combos = (('nccl', 'natural'), ('p2p', 'natural'), ('ce', 'natural'),
+                  ('ce', 'symmetry'), ('nccl', 'symmetry'), ('p2p', 'symmetry'))
+        if quick:
+            combos = (('ce', 'natural'), ('ce', 'symmetry'))
+        for mode, basis in combos:
             sop = ShardedPauliOperator(op, n, dist=dist, mode=mode, basis=basis,
                                        max_staging=1 if mode in ('nccl', 'ce') else None)
             ld = sop.dim
@@ -58,7 +62,8 @@ def main():
     e1 = None
     if rank == 0:
         e1, _ = get_ground_state(LinearQubitOperator(hub, 16))
-    for mode, basis in (('nccl', 'natural'), ('ce', 'natural'), ('ce', 'symmetry')):
+    for mode, basis in ((('ce', 'symmetry'),) if quick else
+                        (('nccl', 'natural'), ('ce', 'natural'), ('ce', 'symmetry'))):
         sop = ShardedPauliOperator(hub, 16, dist=dist, mode=mode, basis=basis)
         stats = {}
         energy, _, residual = lanczos_ground_state(sop, dist, stats=stats)
@@ -69,7 +74,54 @@ def main():
         sop.close()
     if rank == 0:
         print('DIST_CHECK', 'PASS' if ok else 'FAIL')
+    if os.environ.get('OFB_DIST_BENCH_QUBITS'):
+        compare_bases(int(os.environ['OFB_DIST_BENCH_QUBITS']), rank, world, local)
     dist.destroy_process_group()
+
+
+def compare_bases(n, rank, world, local, steps=5, warmup=3):
+    """Same Hubbard H|psi> sharded by the top qubits and by conserved parities, timed back to
+    back in one process group (CUDA events, max over ranks); one JSON line per basis."""
+    import json
+    dims = {16: (2, 4), 20: (2, 5), 24: (3, 4), 28: (2, 7), 30: (3, 5), 32: (4, 4)}[n]
+    model = hamiltonians.hubbard_jw(*dims)
+    comm = TorchComm(dist, 'cuda:%d' % local)
+    for basis in ('natural', 'symmetry'):
+        sop = ShardedPauliOperator(model, n, dist=dist, mode='ce', basis=basis)
+        vin, vout = sop.new_vector(), sop.new_vector()
+        krylov.fill_random(sop.dim, 42 + rank, False, vin.ptr)
+        exchanging = bool(sop.layout.remote_patterns)
+        if exchanging:
+            sop.register_peer_vectors([vin])
+
+        def step():
+            if exchanging:
+                comm.barrier()
+            sop.matvec(vin, vout)
+        for _ in range(warmup):
+            step()
+        torch.cuda.synchronize()
+        dist.barrier()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        for _ in range(steps):
+            step()
+        b.record()
+        torch.cuda.synchronize()
+        t = torch.tensor([a.elapsed_time(b) / steps], dtype=torch.float64, device='cuda')
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        e = krylov.gdot(sop.dim, vin.ptr, vout.ptr, comm)
+        if rank == 0:
+            print(json.dumps({'workload': 'Fermi-Hubbard %dx%d JW, %d qubits' % (dims + (n,)), 'n_gpus': world,
+                              'basis': basis, 'shard_bits': sop.basis.describe(sop.layout.shard_bits),
+                              'peer_shards_per_matvec': len(sop.layout.remote_patterns),
+                              'ms_per_matvec': float(t.item()),
+                              'term_amp_per_s': sop.n_terms * float(1 << n) / (float(t.item()) / 1e3),
+                              'vHv': [e.real, e.imag]}))
+        sop.close()
+        del vin, vout, sop
+        torch.cuda.synchronize()
+        dist.barrier()
 
 
 if __name__ == '__main__':

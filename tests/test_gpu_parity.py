@@ -340,6 +340,20 @@ def test_csc_fermion_route_equals_pauli_route_spectrum():
     assert numpy.allclose(numpy.linalg.eigvalsh(f), numpy.linalg.eigvalsh(q), atol=1e-10)
 
 
+def test_ladder_operator_matrices_match_reference():
+    # jordan_wigner_ladder_sparse (sparse_tools.py:49-73), golden matrices from the reference
+    from openfermion_b200.linalg import jordan_wigner_ladder_sparse
+    data = helpers.golden('ladder_cases.npz')
+    for name in data['names']:
+        n, mode, kind = (int(v) for v in data[name + '/args'])
+        mat = jordan_wigner_ladder_sparse(n, mode, kind)
+        assert mat.shape == (1 << n, 1 << n) and mat.dtype == numpy.complex128
+        helpers.assert_csc_matches(mat, data[name + '/indptr'], data[name + '/indices'],
+                                   data[name + '/data'], rtol=0)
+    with pytest.raises(ValueError):
+        jordan_wigner_ladder_sparse(3, 3, 1)
+
+
 # ---- sharded kernel form on one GPU (virtual ranks) -------------------------------------------
 @pytest.mark.parametrize('basis_kind', ['natural', 'symmetry'])
 @pytest.mark.parametrize('builder,n,world', [(lambda: hamiltonians.hubbard_jw(2, 4), 16, 4),

@@ -79,6 +79,30 @@ def test_oracle_fermion_route_matches_reference(case):
     helpers.assert_csc_matches(mat, case['indptr'], case['indices'], case['data'], rtol=0)
 
 
+def test_oracle_ladder_operator_matches_reference():
+    # jordan_wigner_ladder_sparse (sparse_tools.py:49-73) = the one-factor fermion route
+    data = helpers.golden('ladder_cases.npz')
+    for name in data['names']:
+        n, mode, kind = (int(v) for v in data[name + '/args'])
+        mat = po.jordan_wigner_sparse({((mode, kind),): 1.0}, n)
+        helpers.assert_csc_matches(mat, data[name + '/indptr'], data[name + '/indices'],
+                                   data[name + '/data'], rtol=0)
+
+
+def test_kronecker_helpers_match_reference():
+    # wrapped_kronecker / kronecker_operators (sparse_tools.py:39-46): generic host helpers
+    import scipy.sparse
+    from openfermion_b200.linalg import kronecker_operators, wrapped_kronecker
+    data = helpers.golden('ladder_cases.npz')
+    a, b, c = (scipy.sparse.csc_matrix(data['kron_in_' + t]) for t in 'abc')
+    for tag, mat in (('ab', wrapped_kronecker(a, b)), ('abc', kronecker_operators([a, b, c]))):
+        assert mat.format == 'csc' and tuple(data['kron_%s/shape' % tag]) == mat.shape
+        mat.sort_indices()
+        want = scipy.sparse.csc_matrix((data['kron_%s/data' % tag], data['kron_%s/indices' % tag],
+                                        data['kron_%s/indptr' % tag]), shape=mat.shape)
+        assert abs(mat - want).max() == 0
+
+
 @pytest.mark.parametrize('case', helpers.qubit_cases(), ids=lambda c: c.name)
 def test_c_oracle_matches_numpy_oracle(case):
     op = helpers.qubit_case_operator(case)
