@@ -378,6 +378,8 @@ def main():
     ap.add_argument('--dist-mode', default='ce', choices=['ce', 'nccl', 'p2p'])
     ap.add_argument('--dist-basis', default='symmetry', choices=['symmetry', 'natural'],
                     help='N>1: shard by conserved parities first (no exchange for them) or by the top qubits')
+    ap.add_argument('--dist-order', default='locality', choices=['locality', 'natural'],
+                    help='N>1 with --dist-basis symmetry: order of the qubits inside a shard')
     ap.add_argument('--dist-diagnose', action='store_true')
     args = ap.parse_args()
     if args.impl == 'reference':

@@ -111,7 +111,7 @@ class ShardedPauliOperator:
 
     def __init__(self, operator, n_qubits=None, dist=None, group=None, mode='nccl',
                  max_staging=None, local_apply=None, vector_factory=None, tensor_of=None,
-                 basis='natural'):
+                 basis='natural', local_order='natural'):
         self.dist = dist
         self.group = group
         self.rank = dist.get_rank(group) if dist is not None else 0
@@ -125,11 +125,16 @@ class ShardedPauliOperator:
         # basis: 'natural' = shard by the top qubits; 'symmetry' = shard by conserved parities
         # first (shard_basis.py), which removes peer exchanges; or a ShardBasis instance.
         # Shards then hold psi'[c'] = psi[B^-1 c']: see shard_of / natural_indices.
+        # local_order='locality' (with basis='symmetry') also permutes the qubits inside a
+        # shard so that more x-groups gather from the same cache-resident blocks.
         shard_bits = max(self.world, 1).bit_length() - 1
         if basis == 'natural':
+            if local_order != 'natural':
+                raise ValueError("local_order='locality' needs basis='symmetry'")
             basis = ShardBasis.natural(self.n_qubits)
         elif basis == 'symmetry':
-            basis = ShardBasis.for_sharding(self.n_qubits, min(shard_bits, self.n_qubits), x)
+            basis = ShardBasis.for_sharding(self.n_qubits, min(shard_bits, self.n_qubits), x,
+                                            local_order=local_order)
         elif not isinstance(basis, ShardBasis):
             raise ValueError("basis must be 'natural', 'symmetry' or a ShardBasis")
         if basis.n_qubits != self.n_qubits:
@@ -469,8 +474,10 @@ def bench_main(args, metric, unit, clock_sampler_cls, measured_peak):
         dims = {12: (2, 3), 16: (2, 4), 20: (2, 5), 24: (3, 4), 28: (2, 7), 30: (3, 5)}[sites * 2]
         op_model, name = hamiltonians.hubbard_jw(*dims), 'Fermi-Hubbard %dx%d spinful JW, %d qubits' % (dims + (n,))
     mode = args.dist_mode
-    op = ShardedPauliOperator(op_model, n, dist=dist, mode=mode,
-                              basis=getattr(args, 'dist_basis', 'symmetry'))
+    basis_kind = getattr(args, 'dist_basis', 'symmetry')
+    local_order = getattr(args, 'dist_order', 'locality') if basis_kind == 'symmetry' else 'natural'
+    op = ShardedPauliOperator(op_model, n, dist=dist, mode=mode, basis=basis_kind,
+                              local_order=local_order)
     layout = op.layout
     natural_layout = ShardLayout(n, world, op._natural_x)
     dim_local = op.dim
@@ -583,6 +590,7 @@ def bench_main(args, metric, unit, clock_sampler_cls, measured_peak):
             'config': {'workload': name, 'n_qubits': n, 'terms': T, 'x_groups': G,
                        'sharding': '%d shard bits over %d ranks: %s' % (
                            layout.shard_bits, world, op.basis.describe(layout.shard_bits)),
+                       'local_qubit_order': local_order,
                        'exchange': mode, 'remote_patterns': len(layout.remote_patterns),
                        'remote_patterns_top_qubit_sharding': len(natural_layout.remote_patterns),
                        'exchange_bytes_per_rank_per_step': layout.exchange_bytes_per_matvec() if mode in ('nccl', 'ce') else None,

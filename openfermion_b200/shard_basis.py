@@ -68,6 +68,91 @@ def gf2_nullspace(masks, n_bits):
     return basis
 
 
+def _distinct_outside(groups, low_mask):
+    """Number of distinct parts of the x-masks outside `low_mask`: how many different input
+    blocks (own block included) a block of the index space spanned by `low_mask` gathers from."""
+    return len(numpy.unique(groups & ~numpy.uint64(low_mask)))
+
+
+def _best_subset(groups, pool, size, starts):
+    """Subset of `pool` (bit positions) of the given size minimising _distinct_outside, by
+    steepest-descent swaps from a few deterministic starting sets."""
+    if size >= len(pool):
+        return sorted(pool)
+    best = None
+    for start in starts:
+        cur = sorted(start)[:size]
+        cur += [b for b in pool if b not in cur][:size - len(cur)]
+        mask = sum(1 << b for b in cur)
+        cost = _distinct_outside(groups, mask)
+        improved = True
+        while improved:
+            improved = False
+            move = None
+            for out_bit in cur:
+                base = mask & ~(1 << out_bit)
+                for in_bit in pool:
+                    if (mask >> in_bit) & 1:
+                        continue
+                    c = _distinct_outside(groups, base | (1 << in_bit))
+                    if c < cost:
+                        cost, move = c, (out_bit, in_bit)
+            if move is not None:
+                cur[cur.index(move[0])] = move[1]
+                mask = sum(1 << b for b in cur)
+                improved = True
+        if best is None or cost < best[0]:
+            best = (cost, sorted(cur))
+    return best[1]
+
+
+# Levels of the memory hierarchy the apply kernel (csrc/apply.cu) re-uses input blocks in:
+# a CTA tile of 2^10 amplitudes (L1) and the span of about 2^19 amplitudes that the CTAs in
+# flight keep alive in L2 (profiles/README.md: for the 30-qubit Hubbard model the number of
+# distinct x >> 10 values, 45 of 61 groups, matches the measured L1 miss share and the number
+# of distinct x >> 18..19 values, 27..31, the measured 30 DRAM read streams).
+LOCALITY_LEVELS = (10, 19)
+LOCALITY_MAX_GROUPS = 4096
+
+
+def locality_order(x_masks, n_bits, levels=LOCALITY_LEVELS):
+    """Order of the index bits (a list of natural bit positions, new bit 0 first) that
+    minimises the number of distinct x-mask parts above each level: first the best
+    `levels[-1]`-bit set, then the best `levels[0]` bits inside it; bits keep their natural
+    relative order inside a level.  The natural order is returned when less than 10 % is gained
+    or the Hamiltonian has too many groups for locality to matter (dense molecular masks)."""
+    groups = numpy.unique(numpy.asarray(x_masks, dtype=numpy.uint64))
+    natural = list(range(n_bits))
+    if len(groups) < 2 or len(groups) > LOCALITY_MAX_GROUPS:
+        return natural
+    sizes = [lv for lv in sorted(levels) if lv < n_bits]
+    if not sizes:
+        return natural
+    # greedy forward order as a second starting point
+    greedy, mask = [], 0
+    for _ in range(n_bits):
+        pick = min((b for b in natural if not (mask >> b) & 1),
+                   key=lambda b: (_distinct_outside(groups, mask | (1 << b)), b))
+        greedy.append(pick)
+        mask |= 1 << pick
+    pool = natural
+    nested = []
+    for size in reversed(sizes):
+        chosen = _best_subset(groups, pool, size, [pool, [b for b in greedy if b in pool]])
+        nested.append(chosen)
+        pool = chosen
+    # nested[-1] is the innermost (smallest) set
+    order = list(nested[-1])
+    for outer in reversed(nested[:-1]):
+        order += [b for b in outer if b not in order]
+    order += [b for b in natural if b not in order]
+
+    def costs(o):
+        return tuple(_distinct_outside(groups, sum(1 << b for b in o[:size])) for size in sizes)
+    # re-order only for a clear gain (at least 10 % fewer gathered blocks over the levels)
+    return order if sum(costs(order)) <= 0.9 * sum(costs(natural)) else natural
+
+
 class ShardBasis:
     """c' = B c over GF(2).  `rows[b]` is the mask whose parity with c gives bit b of c';
     `cols[b]` is the natural index of the relabelled basis state 1 << b (column b of B^-1)."""
@@ -115,15 +200,19 @@ class ShardBasis:
         return cls(n_qubits, [1 << b for b in range(n_qubits)])
 
     @classmethod
-    def for_sharding(cls, n_qubits, shard_bits, x_masks):
+    def for_sharding(cls, n_qubits, shard_bits, x_masks, local_order='natural'):
         """Choose the `shard_bits` top rows to minimise the number of distinct non-zero crossing
         patterns (= peer shards pulled per matvec), greedily: conserved parities (null space of
         the x-masks) first, then single qubits, highest first.  Ties go to fewer crossing groups,
         then to the earlier candidate.  The remaining rows keep the other index bits in their
-        natural order, so a shard's local layout is the natural one."""
+        natural order, so a shard's local layout is the natural one -- unless
+        local_order='locality', which also permutes the local bits so that as many x-groups as
+        possible gather from the same cache-resident blocks (`locality_order`)."""
         n = n_qubits
         groups = numpy.unique(numpy.asarray(x_masks, dtype=numpy.uint64))
-        if shard_bits == 0 or n == 0:
+        if local_order not in ('natural', 'locality'):
+            raise ValueError("local_order must be 'natural' or 'locality'")
+        if n == 0 or (shard_bits == 0 and local_order == 'natural'):
             return cls.natural(n)
         candidates = gf2_nullspace(groups.tolist(), n) + [1 << b for b in range(n - 1, -1, -1)]
         chosen, echelon = [], {}
@@ -152,7 +241,15 @@ class ShardBasis:
         kept = [b for b in range(n - 1, -1, -1) if b not in echelon]
         rows_top_down = chosen + [1 << b for b in kept]
         assert len(pivots) == shard_bits and len(rows_top_down) == n
-        return cls(n, rows_top_down[::-1])
+        basis = cls(n, rows_top_down[::-1])
+        if local_order == 'locality':
+            # order the local bits by the x-masks as the kernels will see them
+            local_bits = n - shard_bits
+            local_x = basis.to_basis_index(groups) & numpy.uint64((1 << local_bits) - 1)
+            order = locality_order(local_x, local_bits)
+            rows = [basis.rows[b] for b in order] + basis.rows[local_bits:]
+            basis = cls(n, rows)
+        return basis
 
     # -- indices ---------------------------------------------------------------------------
     def _apply(self, table, index):

@@ -24,6 +24,7 @@ def main():
     ap.add_argument('--y', type=int, default=4)
     ap.add_argument('--mode', default='ce')
     ap.add_argument('--basis', default='symmetry', choices=['symmetry', 'natural'])
+    ap.add_argument('--order', default='locality', choices=['locality', 'natural'])
     ap.add_argument('--tol', type=float, default=1e-8)
     ap.add_argument('--krylov', type=int, default=120)
     args = ap.parse_args()
@@ -32,7 +33,8 @@ def main():
     dist = init_nccl(local)
     _lib.call('ofb_set_device', ctypes.c_int(local))
     op = hamiltonians.hubbard_jw(args.x, args.y)
-    sop = ShardedPauliOperator(op, op.n_qubits, dist=dist, mode=args.mode, basis=args.basis)
+    sop = ShardedPauliOperator(op, op.n_qubits, dist=dist, mode=args.mode, basis=args.basis,
+                               local_order=args.order if args.basis == 'symmetry' else 'natural')
     stats = {}
     import torch
     torch.cuda.synchronize()

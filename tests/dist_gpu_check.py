@@ -86,8 +86,8 @@ def compare_bases(n, rank, world, local, steps=5, warmup=3):
     dims = {16: (2, 4), 20: (2, 5), 24: (3, 4), 28: (2, 7), 30: (3, 5), 32: (4, 4)}[n]
     model = hamiltonians.hubbard_jw(*dims)
     comm = TorchComm(dist, 'cuda:%d' % local)
-    for basis in ('natural', 'symmetry'):
-        sop = ShardedPauliOperator(model, n, dist=dist, mode='ce', basis=basis)
+    for basis, local_order in (('natural', 'natural'), ('symmetry', 'natural'), ('symmetry', 'locality')):
+        sop = ShardedPauliOperator(model, n, dist=dist, mode='ce', basis=basis, local_order=local_order)
         vin, vout = sop.new_vector(), sop.new_vector()
         krylov.fill_random(sop.dim, 42 + rank, False, vin.ptr)
         exchanging = bool(sop.layout.remote_patterns)
@@ -113,7 +113,7 @@ def compare_bases(n, rank, world, local, steps=5, warmup=3):
         e = krylov.gdot(sop.dim, vin.ptr, vout.ptr, comm)
         if rank == 0:
             print(json.dumps({'workload': 'Fermi-Hubbard %dx%d JW, %d qubits' % (dims + (n,)), 'n_gpus': world,
-                              'basis': basis, 'shard_bits': sop.basis.describe(sop.layout.shard_bits),
+                              'basis': basis, 'local_qubit_order': local_order, 'shard_bits': sop.basis.describe(sop.layout.shard_bits),
                               'peer_shards_per_matvec': len(sop.layout.remote_patterns),
                               'ms_per_matvec': float(t.item()),
                               'term_amp_per_s': sop.n_terms * float(1 << n) / (float(t.item()) / 1e3),

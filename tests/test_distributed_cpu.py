@@ -41,7 +41,7 @@ def _make_operator(kind):
     return op, 6
 
 
-def _worker(rank, world, port, kind, depth, out_dir, basis='natural'):
+def _worker(rank, world, port, kind, depth, out_dir, basis='natural', local_order='natural'):
     os.environ['MASTER_ADDR'] = '127.0.0.1'
     os.environ['MASTER_PORT'] = str(port)
     dist.init_process_group('gloo', rank=rank, world_size=world)
@@ -71,7 +71,8 @@ def _worker(rank, world, port, kind, depth, out_dir, basis='natural'):
         op = ShardedPauliOperator(
             operator, n, dist=dist, mode='nccl', max_staging=depth, local_apply=local_apply,
             vector_factory=lambda: _HostVec(1 << (n - (world.bit_length() - 1))),
-            tensor_of=lambda v: torch.from_numpy(v.array.view(numpy.float64)), basis=basis)
+            tensor_of=lambda v: torch.from_numpy(v.array.view(numpy.float64)), basis=basis,
+            local_order=local_order)
         layout = op.layout
         ld = layout.local_dim
         j = numpy.arange(ld, dtype=numpy.uint64)
@@ -115,13 +116,15 @@ def test_sharded_matvec_over_gloo(world, kind, depth, tmp_path):
         assert dot_err < 1e-11
 
 
+@pytest.mark.parametrize('local_order', ['natural', 'locality'])
 @pytest.mark.parametrize('world,kind,remote', [(2, 'hubbard', 0), (4, 'hubbard', 0), (8, 'hubbard', 1),
                                                (4, 'complex', None), (2, 'small', 0)])
-def test_symmetry_basis_sharded_matvec_over_gloo(world, kind, remote, tmp_path):
+def test_symmetry_basis_sharded_matvec_over_gloo(world, kind, remote, local_order, tmp_path):
     """Sharding by conserved parities (shard_basis.py): same H|psi> after relabelling, and the
     spin-parity bits of a Hubbard model need no peer shard at all."""
     port = _free_port()
-    mp.start_processes(_worker, args=(world, port, kind, None, str(tmp_path), 'symmetry'), nprocs=world,
+    mp.start_processes(_worker, args=(world, port, kind, None, str(tmp_path), 'symmetry', local_order),
+                       nprocs=world,
                        join=True, start_method='fork')
     for rank in range(world):
         err, ok_cover, ok_flags, dot_err, n_remote, tiled = numpy.load(tmp_path / ('r%d.npy' % rank))

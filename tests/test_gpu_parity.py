@@ -355,7 +355,7 @@ def test_ladder_operator_matrices_match_reference():
 
 
 # ---- sharded kernel form on one GPU (virtual ranks) -------------------------------------------
-@pytest.mark.parametrize('basis_kind', ['natural', 'symmetry'])
+@pytest.mark.parametrize('basis_kind', ['natural', 'symmetry', 'symmetry+locality'])
 @pytest.mark.parametrize('builder,n,world', [(lambda: hamiltonians.hubbard_jw(2, 4), 16, 4),
                                              (lambda: hamiltonians.hubbard_jw(2, 4), 16, 8),
                                              (lambda: hamiltonians.molecular_jw(6, seed=1234), 12, 8),
@@ -378,7 +378,8 @@ def test_virtual_rank_sharding_matches_unsharded(builder, n, world, basis_kind):
     if basis_kind == 'natural':
         basis, plan = ShardBasis.natural(n), lin.plan
     else:
-        basis = ShardBasis.for_sharding(n, world.bit_length() - 1, x)
+        basis = ShardBasis.for_sharding(n, world.bit_length() - 1, x,
+                                        local_order='locality' if 'locality' in basis_kind else 'natural')
         x, z, c = basis.transform_terms(x, z, c)
         plan = PauliPlan(n, x, z, c)
     layout = ShardLayout(n, world, x)

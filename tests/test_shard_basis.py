@@ -10,7 +10,7 @@ from openfermion_b200 import hamiltonians
 from openfermion_b200.compiler import compile_qubit_operator
 from openfermion_b200.distributed import ShardLayout
 from openfermion_b200.ops import QubitOperator
-from openfermion_b200.shard_basis import ShardBasis, gf2_nullspace
+from openfermion_b200.shard_basis import ShardBasis, _distinct_outside, gf2_nullspace, locality_order
 
 
 def _gather_apply(n, x, z, c, v):
@@ -74,9 +74,10 @@ def test_singular_basis_is_rejected():
         ShardBasis(3, [1, 2])
 
 
+@pytest.mark.parametrize('local_order', ['natural', 'locality'])
 @pytest.mark.parametrize('kind', ['hubbard', 'hubbard_bk', 'molecular', 'molecular_bk', 'complex', 'ys'])
-@pytest.mark.parametrize('shard_bits', [1, 2, 3])
-def test_relabelled_table_is_the_same_operator(kind, shard_bits):
+@pytest.mark.parametrize('shard_bits', [0, 1, 2, 3])
+def test_relabelled_table_is_the_same_operator(kind, shard_bits, local_order):
     if kind == 'hubbard':
         op, n = hamiltonians.hubbard_jw(2, 2, chemical_potential=0.3, magnetic_field=0.2), 8
     elif kind == 'hubbard_bk':
@@ -92,7 +93,7 @@ def test_relabelled_table_is_the_same_operator(kind, shard_bits):
             + QubitOperator('Y1 Y2 Y4 Y6', 0.75j) + QubitOperator('X0 Y2 Z3', 1.0) + QubitOperator('Z1 Z6', 3.0)
         n = 7
     x, z, c = compile_qubit_operator(op, n)
-    basis = ShardBasis.for_sharding(n, shard_bits, x)
+    basis = ShardBasis.for_sharding(n, shard_bits, x, local_order=local_order)
     xp, zp, cp = basis.transform_terms(x, z, c)
     rng = numpy.random.default_rng(5)
     v = rng.normal(size=1 << n) + 1j * rng.normal(size=1 << n)
@@ -102,9 +103,38 @@ def test_relabelled_table_is_the_same_operator(kind, shard_bits):
     # never more peer shards than sharding by the top qubits
     world = 1 << shard_bits
     assert len(ShardLayout(n, world, xp).remote_patterns) <= len(ShardLayout(n, world, x).remote_patterns)
-    # the non-shard bits keep their natural order: local part of c' = surviving bits of c
+    # the non-shard bits are single qubits; in their natural order unless re-ordered for locality
     local_rows = basis.rows[:n - shard_bits]
-    assert all(bin(r).count('1') == 1 for r in local_rows) and local_rows == sorted(local_rows)
+    assert all(bin(r).count('1') == 1 for r in local_rows)
+    if local_order == 'natural':
+        assert local_rows == sorted(local_rows)
+    else:
+        assert basis.rows[n - shard_bits:] == ShardBasis.for_sharding(n, shard_bits, x).rows[n - shard_bits:]
+
+
+def test_locality_order_reduces_distinct_gather_blocks():
+    """The qubit order inside a shard is chosen to minimise the number of distinct x-mask parts
+    above the L1 tile (2^10 amplitudes) and above the L2 span (2^19): the model that matches the
+    measured L1 miss share and DRAM streams of the Hubbard runs (profiles/README.md)."""
+    op = hamiltonians.hubbard_jw(4, 4)
+    x, z, c = compile_qubit_operator(op, 32)
+    for shard_bits, natural_costs in ((0, (51, 30)), (3, (43, 19))):
+        local = 32 - shard_bits
+        costs = []
+        for local_order in ('natural', 'locality'):
+            basis = ShardBasis.for_sharding(32, shard_bits, x, local_order=local_order)
+            xp, _, _ = basis.transform_terms(x, z, c)
+            g = numpy.unique(xp & numpy.uint64((1 << local) - 1))
+            costs.append((_distinct_outside(g, (1 << 10) - 1), _distinct_outside(g, (1 << 19) - 1)))
+        assert costs[0] == natural_costs
+        assert costs[1][0] <= 0.8 * costs[0][0] and costs[1][1] <= 0.65 * costs[0][1]
+    # deterministic, a permutation, and the identity when nothing can be gained
+    order = locality_order(numpy.unique(x), 32)
+    assert order == locality_order(numpy.unique(x), 32) and sorted(order) == list(range(32))
+    assert locality_order(numpy.array([0, 1, 2, 3], dtype=numpy.uint64), 12) == list(range(12))
+    dense = hamiltonians.molecular_jw(10, seed=1234)  # 2 536 groups: nothing to gain, natural order kept
+    xd, _ = dense.index_masks(20)
+    assert ShardBasis.for_sharding(20, 0, xd, local_order='locality').identity
 
 
 def test_conserved_parities_remove_the_exchange():
