@@ -184,6 +184,7 @@ int ofb_csc_count(ofb_plan *p, int64_t *nnz, int *index_bits, void *stream) {
     uint32_t *bitmap = p->d_bitmap, *prefix = p->d_bitmap + (size_t)words * dim;
     // group descriptors for projected plans are not uploaded by plan_create: build on demand
     if (!p->d_groups) {
+        OFB_TRY
         std::vector<GroupDesc> groups(p->n_groups);
         for (int64_t g = 0; g < p->n_groups; ++g)
             groups[g] = GroupDesc{p->h_group_x[g], p->h_group_begin[g],
@@ -192,6 +193,7 @@ int ofb_csc_count(ofb_plan *p, int64_t *nnz, int *index_bits, void *stream) {
         if (!groups.empty())
             OFB_CUDA(cudaMemcpy(p->d_groups, groups.data(), groups.size() * sizeof(GroupDesc),
                                 cudaMemcpyHostToDevice));
+        OFB_CATCH((void)0)
     }
     if (p->csc_mode == 1) {
         int rc = csc_exact_count(p, counts, s);

@@ -4,6 +4,8 @@
 #include <stdint.h>
 
 #include <atomic>
+#include <new>
+#include <stdexcept>
 #include <string>
 #include <vector>
 
@@ -22,6 +24,20 @@ extern std::atomic<int64_t> g_launches;
         cudaError_t e__ = (call);                                               \
         if (e__ != cudaSuccess) return ofb::cuda_fail(e__, #call, __FILE__, __LINE__); \
     } while (0)
+
+// No C++ exception may cross the C ABI: entry points that allocate host memory wrap their body
+// in OFB_TRY / OFB_CATCH(cleanup) and turn std::bad_alloc & co. into a status + message.
+#define OFB_TRY try {
+#define OFB_CATCH(cleanup)                                                                  \
+    }                                                                                       \
+    catch (const std::bad_alloc &) {                                                        \
+        cleanup;                                                                            \
+        return ofb::fail(OFB_ERR_NOMEM, "host allocation failed");                          \
+    }                                                                                       \
+    catch (const std::exception &e__) {                                                     \
+        cleanup;                                                                            \
+        return ofb::fail(OFB_ERR_STATE, std::string("internal error: ") + e__.what());      \
+    }
 
 #define OFB_LAUNCH_CHECK()                              \
     do {                                                \

@@ -280,6 +280,8 @@ int ofb_plan_create(int n_qubits, int64_t n_terms, const uint64_t *x_mask, const
                     const double *coeff_ri, int device, ofb_plan **plan) {
     if (!plan) return fail(OFB_ERR_INVALID, "plan is NULL");
     *plan = nullptr;
+    ofb_plan *p = nullptr;
+    OFB_TRY
     if (n_qubits < 0 || n_qubits > 40) return fail(OFB_ERR_INVALID, "n_qubits out of range [0, 40]");
     if (n_terms < 0 || n_terms >= (1ll << 30)) return fail(OFB_ERR_INVALID, "n_terms out of range");
     if (n_terms > 0 && (!x_mask || !z_mask || !coeff_ri))
@@ -289,7 +291,7 @@ int ofb_plan_create(int n_qubits, int64_t n_terms, const uint64_t *x_mask, const
         if ((x_mask[t] | z_mask[t]) & ~full)
             return fail(OFB_ERR_INVALID, "term " + std::to_string(t) + " acts outside n_qubits");
     OFB_CUDA(cudaSetDevice(device));
-    ofb_plan *p = new (std::nothrow) ofb_plan();
+    p = new (std::nothrow) ofb_plan();
     if (!p) return fail(OFB_ERR_NOMEM, "host allocation failed");
     p->n_qubits = n_qubits;
     p->device = device;
@@ -421,6 +423,7 @@ int ofb_plan_create(int n_qubits, int64_t n_terms, const uint64_t *x_mask, const
     }
     *plan = p;
     return OFB_OK;
+    OFB_CATCH(ofb_plan_destroy(p))
 }
 
 int ofb_plan_create_projected(int n_qubits, int64_t n_rows, const uint64_t *occ_mask,
@@ -429,6 +432,8 @@ int ofb_plan_create_projected(int n_qubits, int64_t n_rows, const uint64_t *occ_
                               ofb_plan **plan) {
     if (!plan) return fail(OFB_ERR_INVALID, "plan is NULL");
     *plan = nullptr;
+    ofb_plan *p = nullptr;
+    OFB_TRY
     if (n_qubits < 0 || n_qubits > 40) return fail(OFB_ERR_INVALID, "n_qubits out of range [0, 40]");
     if (n_rows < 0 || n_rows >= (1ll << 30)) return fail(OFB_ERR_INVALID, "n_rows out of range");
     if (n_rows > 0 && (!occ_mask || !occ_val || !x_mask || !z_mask || !coeff_ri))
@@ -438,7 +443,7 @@ int ofb_plan_create_projected(int n_qubits, int64_t n_rows, const uint64_t *occ_
         if ((x_mask[t] | z_mask[t] | occ_mask[t] | occ_val[t]) & ~full)
             return fail(OFB_ERR_INVALID, "row " + std::to_string(t) + " acts outside n_qubits");
     OFB_CUDA(cudaSetDevice(device));
-    ofb_plan *p = new (std::nothrow) ofb_plan();
+    p = new (std::nothrow) ofb_plan();
     if (!p) return fail(OFB_ERR_NOMEM, "host allocation failed");
     p->n_qubits = n_qubits;
     p->device = device;
@@ -460,6 +465,7 @@ int ofb_plan_create_projected(int n_qubits, int64_t n_rows, const uint64_t *occ_
     }
     *plan = p;
     return OFB_OK;
+    OFB_CATCH(ofb_plan_destroy(p))
 }
 
 int ofb_plan_destroy(ofb_plan *p) {

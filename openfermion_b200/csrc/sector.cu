@@ -599,6 +599,8 @@ int ofb_sector_create_tables(int n_qubits, int lo_bits, int n_classes, uint64_t 
                              const int32_t *value, int64_t dim, int device, ofb_sector **sector) {
     if (!sector) return fail(OFB_ERR_INVALID, "sector is NULL");
     *sector = nullptr;
+    ofb_sector *s = nullptr;
+    OFB_TRY
     if (n_qubits < 1 || n_qubits > 40) return fail(OFB_ERR_INVALID, "n_qubits out of range [1, 40]");
     if (lo_bits < 0 || lo_bits > n_qubits || lo_bits > 26 || n_qubits - lo_bits > 26)
         return fail(OFB_ERR_INVALID, "bad lo_bits");
@@ -609,7 +611,7 @@ int ofb_sector_create_tables(int n_qubits, int lo_bits, int n_classes, uint64_t 
         return fail(OFB_ERR_INVALID, "NULL table");
     if (dim < 0 || dim > (1ll << 33)) return fail(OFB_ERR_INVALID, "sector dimension out of range");
     OFB_CUDA(cudaSetDevice(device));
-    ofb_sector *s = new (std::nothrow) ofb_sector();
+    s = new (std::nothrow) ofb_sector();
     if (!s) return fail(OFB_ERR_NOMEM, "host allocation failed");
     s->n_qubits = n_qubits;
     s->device = device;
@@ -672,12 +674,15 @@ int ofb_sector_create_tables(int n_qubits, int lo_bits, int n_classes, uint64_t 
     }
     *sector = s;
     return OFB_OK;
+    OFB_CATCH(ofb_sector_destroy(s))
 }
 
 int ofb_sector_create_list(int n_qubits, int64_t dim, const uint64_t *h_basis, int device,
                            ofb_sector **sector) {
     if (!sector) return fail(OFB_ERR_INVALID, "sector is NULL");
     *sector = nullptr;
+    ofb_sector *s = nullptr;
+    OFB_TRY
     if (n_qubits < 0 || n_qubits > 40) return fail(OFB_ERR_INVALID, "n_qubits out of range [0, 40]");
     if (dim < 0 || dim >= (1ll << 32)) return fail(OFB_ERR_INVALID, "basis list too long");
     if (dim > 0 && !h_basis) return fail(OFB_ERR_INVALID, "NULL basis");
@@ -694,7 +699,7 @@ int ofb_sector_create_list(int n_qubits, int64_t dim, const uint64_t *h_basis, i
         if (k > 0 && sorted[k] == sorted[k - 1]) return fail(OFB_ERR_INVALID, "duplicate basis state");
     }
     OFB_CUDA(cudaSetDevice(device));
-    ofb_sector *s = new (std::nothrow) ofb_sector();
+    s = new (std::nothrow) ofb_sector();
     if (!s) return fail(OFB_ERR_NOMEM, "host allocation failed");
     s->n_qubits = n_qubits;
     s->device = device;
@@ -721,6 +726,7 @@ int ofb_sector_create_list(int n_qubits, int64_t dim, const uint64_t *h_basis, i
     d.dim = dim;
     *sector = s;
     return OFB_OK;
+    OFB_CATCH(ofb_sector_destroy(s))
 }
 
 int ofb_sector_destroy(ofb_sector *s) {
@@ -873,6 +879,7 @@ int ofb_sector_scatter(ofb_sector *s, const void *d_sector, void *d_full, void *
 
 static int sector_ensure_groups(ofb_plan *p) {
     if (p->d_groups) return OFB_OK;
+    OFB_TRY
     std::vector<GroupDesc> groups(p->n_groups);
     for (int64_t g = 0; g < p->n_groups; ++g)
         groups[g] = GroupDesc{p->h_group_x[g], p->h_group_begin[g],
@@ -882,6 +889,7 @@ static int sector_ensure_groups(ofb_plan *p) {
         OFB_CUDA(cudaMemcpy(p->d_groups, groups.data(), groups.size() * sizeof(GroupDesc),
                             cudaMemcpyHostToDevice));
     return OFB_OK;
+    OFB_CATCH((void)0)
 }
 
 int ofb_sector_csc_count(ofb_plan *p, ofb_sector *s, int64_t *nnz, int *index_bits, void *stream) {
