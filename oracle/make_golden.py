@@ -377,11 +377,80 @@ def ladder_cases():
     print('ladder_cases:', len(names), 'cases')
 
 
+def large_state(n, seed):
+    """Seeded normalised input of the large cases; tests/helpers.py:large_state is the same code."""
+    rng = numpy.random.default_rng(seed)
+    v = rng.normal(size=2**n) + 1j * rng.normal(size=2**n)
+    return v / numpy.linalg.norm(v)
+
+
+def large_cases():
+    """The parity ladder of SURVEY.md section 8d above the sizes whose full outputs fit a fixture:
+    the real reference's LinearQubitOperator._matvec, expectation and diagonal at 14-20 qubits --
+    the sizes at which the tiled CUDA kernel (not the small-state kernel) runs.  Stored: the
+    operator, the input's seed and sha256, 2 048 sampled output amplitudes, <v|Hv>, |Hv| and
+    sum(Hv); the diagonal likewise.  The numpy and C oracles are checked on the way."""
+    import time
+    import c_oracle
+    from openfermion_b200 import compiler
+    cases = {}
+    names = []
+    ops = {
+        'hubbard_2x4_jw_n16': (jordan_wigner(fermi_hubbard(2, 4, 1.0, 4.0)), 16),
+        'hubbard_2x5_jw_n20': (jordan_wigner(fermi_hubbard(2, 5, 1.0, 4.0)), 20),
+        'hubbard_2x4_bk_n16': (bravyi_kitaev(fermi_hubbard(2, 4, 1.0, 4.0, 0.3, 0.2)), 16),
+        'molecular_7_jw_n14': (jordan_wigner(random_interaction_operator(7, expand_spin=True, real=True, seed=1234)), 14),
+        'molecular_4_complex_bk_n8_padded_n15': (bravyi_kitaev(get_fermion_operator(
+            random_interaction_operator(8, expand_spin=False, real=False, seed=21))), 15),
+        'molecular_8_jw_n16': (jordan_wigner(random_interaction_operator(8, expand_spin=True, real=True, seed=1234)), 16),
+        # BASELINE.json config 3 at full size: one H|psi> of the real reference (minutes)
+        'hubbard_3x4_jw_n24': (jordan_wigner(fermi_hubbard(3, 4, 1.0, 4.0)), 24),
+    }
+    rng = numpy.random.default_rng(99)
+    for k, (name, (op, n)) in enumerate(ops.items()):
+        seed = 1000 + k
+        v = large_state(n, seed)
+        t0 = time.time()
+        ref_mv = LinearQubitOperator(op, n) * v
+        t_ref = time.time() - t0
+        strs, coeffs, is_complex = pack_terms(op.terms, qubit_term_str)
+        x, z, c = compiler.compile_qubit_terms(op.terms, n)
+        got_c = c_oracle.matvec(n, x, z, c, v)
+        scale = numpy.max(numpy.abs(ref_mv))
+        assert numpy.max(numpy.abs(got_c - ref_mv)) <= 1e-13 * scale, name
+        if len(op.terms) <= 200 and n <= 20:  # the numpy port walks the same ~20 passes per term
+            assert numpy.array_equal(po.matvec(op.terms, n, v), ref_mv), name
+        sample = numpy.sort(rng.choice(2**n, size=2048, replace=False))
+        cases[name + '/terms'] = strs
+        cases[name + '/coeffs'] = coeffs
+        cases[name + '/coeff_is_complex'] = is_complex
+        cases[name + '/n_qubits'] = numpy.array(n)
+        cases[name + '/seed'] = numpy.array(seed)
+        cases[name + '/vec_sha256'] = numpy.array(sha(v))
+        cases[name + '/sample_index'] = sample
+        cases[name + '/sample_matvec'] = ref_mv[sample]
+        cases[name + '/expectation'] = numpy.array(numpy.vdot(v, ref_mv))
+        cases[name + '/norm'] = numpy.array(numpy.linalg.norm(ref_mv))
+        cases[name + '/sum'] = numpy.array(numpy.sum(ref_mv))
+        cases[name + '/max_abs'] = numpy.array(scale)
+        if not is_complex.any() and n <= 16:
+            ref_diag = get_linear_qubit_operator_diagonal(op, n)
+            cases[name + '/sample_diagonal'] = ref_diag[sample]
+            cases[name + '/diagonal_sum'] = numpy.array(numpy.sum(ref_diag))
+        names.append(name)
+        print('  %s: T = %d, reference matvec %.1f s' % (name, len(op.terms), t_ref))
+    cases['names'] = numpy.array(names, dtype=str)
+    numpy.savez_compressed(os.path.join(GOLDEN, 'large_cases.npz'), **cases)
+    print('large_cases:', len(names), 'cases')
+
+
 if __name__ == '__main__':
     os.makedirs(GOLDEN, exist_ok=True)
     which = sys.argv[1:] or ['qubit', 'fermion', 'lih', 'sector', 'files', 'ladder']
     if 'ladder' in which:
         ladder_cases()
+    if 'large' in which:  # minutes of reference time: not part of the default set
+        large_cases()
     if 'qubit' in which:
         qubit_cases()
     if 'fermion' in which:

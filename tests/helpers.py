@@ -64,6 +64,18 @@ def qubit_cases():
     return [Case(data, str(n)) for n in data['names']]
 
 
+def large_cases():
+    data = golden('large_cases.npz')
+    return [Case(data, str(n)) for n in data['names']]
+
+
+def large_state(n, seed):
+    """Seeded normalised input of the large golden cases (oracle/make_golden.py:large_state)."""
+    rng = numpy.random.default_rng(seed)
+    v = rng.normal(size=2**n) + 1j * rng.normal(size=2**n)
+    return v / numpy.linalg.norm(v)
+
+
 def fermion_cases():
     data = golden('fermion_cases.npz')
     return [Case(data, str(n)) for n in data['names']]

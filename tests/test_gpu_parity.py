@@ -226,6 +226,30 @@ def test_matvec_and_expectation_vs_c_oracle(name, builder):
         assert helpers.close(get_linear_qubit_operator_diagonal(op, n), c_oracle.diagonal(n, x, z, c), RTOL)
 
 
+@pytest.mark.parametrize('case', helpers.large_cases(), ids=lambda c: c.name)
+def test_matvec_matches_reference_samples_at_tiled_kernel_sizes(case):
+    """Sampled outputs of the REAL reference's LinearQubitOperator._matvec at 14-24 qubits
+    (tests/golden/large_cases.npz, SURVEY.md section 8d parity ladder): the tiled kernel against
+    the reference itself, 1e-12 relative to max |H v|; expectation and diagonal likewise."""
+    n = case.n
+    v = helpers.large_state(n, int(case['seed']))
+    op = helpers.qubit_case_operator(case)
+    lin = LinearQubitOperator(op, n)
+    got = lin * v
+    scale = float(case['max_abs'])
+    sample = case['sample_index']
+    assert numpy.max(numpy.abs(got[sample] - case['sample_matvec'])) <= RTOL * scale
+    assert abs(numpy.linalg.norm(got) - float(case['norm'])) <= RTOL * float(case['norm'])
+    assert abs(numpy.sum(got) - complex(case['sum'])) <= 1e-10 * float(case['norm']) * 2.0 ** (n / 2)
+    one_norm = float(numpy.sum(numpy.abs(case['coeffs'])))  # bound of |<v|H|v>| for normalised v
+    assert abs(expectation(lin, v) - complex(case['expectation'])) <= RTOL * one_norm
+    if case.has('sample_diagonal'):
+        diag = get_linear_qubit_operator_diagonal(op, n)
+        assert diag.dtype == numpy.float64
+        assert numpy.max(numpy.abs(diag[sample] - case['sample_diagonal'])) <= RTOL * numpy.max(numpy.abs(diag))
+        assert abs(numpy.sum(diag) - float(case['diagonal_sum'])) <= 1e-10 * numpy.sum(numpy.abs(diag))
+
+
 def test_matvec_accepts_reference_input_kinds():
     op = hamiltonians.hubbard_jw(2, 2)
     lin = LinearQubitOperator(op, 8)

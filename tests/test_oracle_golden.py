@@ -113,6 +113,29 @@ def test_c_oracle_matches_numpy_oracle(case):
         assert helpers.close(c_oracle.diagonal(case.n, x, z, c), case['diagonal'], 1e-15)
 
 
+@pytest.mark.parametrize('case', helpers.large_cases(), ids=lambda c: c.name)
+def test_c_oracle_matches_reference_at_tiled_kernel_sizes(case):
+    """SURVEY.md section 8d parity ladder: sampled outputs of the real reference's matvec at
+    14-24 qubits (tests/golden/large_cases.npz) pin the C oracle at the sizes the tiled CUDA
+    kernel runs at; the GPU suite checks the kernel against the same samples."""
+    import hashlib
+    n = case.n
+    v = helpers.large_state(n, int(case['seed']))
+    assert hashlib.sha256(numpy.ascontiguousarray(v).tobytes()).hexdigest() == str(case['vec_sha256'])
+    op = helpers.qubit_case_operator(case)
+    x, z, c = compiler.compile_qubit_terms(op.terms, n)
+    got = c_oracle.matvec(n, x, z, c, v)
+    scale = float(case['max_abs'])
+    sample = case['sample_index']
+    assert numpy.max(numpy.abs(got[sample] - case['sample_matvec'])) <= 1e-13 * scale
+    one_norm = float(numpy.sum(numpy.abs(case['coeffs'])))
+    assert abs(numpy.vdot(v, got) - complex(case['expectation'])) <= 1e-13 * one_norm
+    assert abs(numpy.linalg.norm(got) - float(case['norm'])) <= 1e-12 * float(case['norm'])
+    if case.has('sample_diagonal'):
+        diag = c_oracle.diagonal(n, x, z, c)
+        assert numpy.max(numpy.abs(diag[sample] - case['sample_diagonal'])) <= 1e-13 * numpy.max(numpy.abs(diag))
+
+
 def test_ground_state_known_answer():
     # sparse_tools_test.py:593-604
     op = QubitOperator('Y0 X1') + QubitOperator('Z0 Z1')
