@@ -444,6 +444,61 @@ def large_cases():
     print('large_cases:', len(names), 'cases')
 
 
+def csc_ladder_cases():
+    """CSC parity ladder (the real reference up to n = 14 molecular,
+    n = 16 Hubbard): the reference's own matrices by sha256 of indptr / indices / data, plus
+    sampled entries so that a mismatch can be located.  Pauli route and fermion route."""
+    import time
+    cases = {}
+    names = []
+    mol6 = random_interaction_operator(6, expand_spin=True, real=True, seed=7)
+    mol7 = random_interaction_operator(7, expand_spin=True, real=True, seed=1234)
+    todo = {
+        'pauli/hubbard_2x4_jw_n16': ('pauli', jordan_wigner(fermi_hubbard(2, 4, 1.0, 4.0)), 16),
+        'pauli/hubbard_2x4_bk_n16': ('pauli', bravyi_kitaev(fermi_hubbard(2, 4, 1.0, 4.0)), 16),
+        'fermion/hubbard_2x4_mu_h_n16': ('fermion', fermi_hubbard(2, 4, 1.0, 4.0, 0.3, 0.2), 16),
+        'pauli/molecular_6_jw_n12': ('pauli', jordan_wigner(mol6), 12),
+        'fermion/molecular_6_n12': ('fermion', get_fermion_operator(mol6), 12),
+        'pauli/molecular_7_jw_n14': ('pauli', jordan_wigner(mol7), 14),
+        'fermion/molecular_7_n14': ('fermion', get_fermion_operator(mol7), 14),
+    }
+    rng = numpy.random.default_rng(5)
+    for name, (route, op, n) in todo.items():
+        t0 = time.time()
+        if route == 'pauli':
+            ref = qubit_operator_sparse(op, n)
+            strs, coeffs, is_complex = pack_terms(op.terms, qubit_term_str)
+        else:
+            ref = jordan_wigner_sparse(op, n)
+            strs, coeffs, is_complex = pack_terms(op.terms, fermion_term_str)
+        dt = time.time() - t0
+        if n <= 12:  # the scipy-based oracle needs the same triplet memory as the reference
+            mine = po.qubit_operator_sparse(op.terms, n) if route == 'pauli' else po.jordan_wigner_sparse(op.terms, n)
+            assert same_csc(ref, mine), name
+        key = name.replace('/', '__')
+        sample = numpy.sort(rng.choice(ref.nnz, size=min(4096, ref.nnz), replace=False))
+        cases[key + '/route'] = numpy.array(route)
+        cases[key + '/terms'] = strs
+        cases[key + '/coeffs'] = coeffs
+        cases[key + '/coeff_is_complex'] = is_complex
+        cases[key + '/n_qubits'] = numpy.array(n)
+        cases[key + '/nnz'] = numpy.array(ref.nnz)
+        cases[key + '/index_dtype'] = numpy.array(str(ref.indices.dtype))
+        cases[key + '/indptr_sha256'] = numpy.array(sha(ref.indptr))
+        cases[key + '/indices_sha256'] = numpy.array(sha(ref.indices))
+        cases[key + '/data_sha256'] = numpy.array(sha(ref.data))
+        cases[key + '/sample_position'] = sample
+        cases[key + '/sample_indices'] = ref.indices[sample]
+        cases[key + '/sample_data'] = ref.data[sample]
+        cases[key + '/colcount_head'] = numpy.diff(ref.indptr)[:256]
+        cases[key + '/data_abs_sum'] = numpy.array(numpy.abs(ref.data).sum())
+        names.append(key)
+        print('  %s: T = %d, nnz = %d, reference %.1f s' % (name, len(op.terms), ref.nnz, dt))
+    cases['names'] = numpy.array(names, dtype=str)
+    numpy.savez_compressed(os.path.join(GOLDEN, 'csc_ladder_cases.npz'), **cases)
+    print('csc_ladder_cases:', len(names), 'cases')
+
+
 if __name__ == '__main__':
     os.makedirs(GOLDEN, exist_ok=True)
     which = sys.argv[1:] or ['qubit', 'fermion', 'lih', 'sector', 'files', 'ladder']
@@ -451,6 +506,8 @@ if __name__ == '__main__':
         ladder_cases()
     if 'large' in which:  # minutes of reference time: not part of the default set
         large_cases()
+    if 'csc_ladder' in which:  # gigabytes of triplets in the reference: not part of the default set
+        csc_ladder_cases()
     if 'qubit' in which:
         qubit_cases()
     if 'fermion' in which:

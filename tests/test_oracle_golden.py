@@ -136,6 +136,32 @@ def test_c_oracle_matches_reference_at_tiled_kernel_sizes(case):
         assert numpy.max(numpy.abs(diag[sample] - case['sample_diagonal'])) <= 1e-13 * numpy.max(numpy.abs(diag))
 
 
+def _csc_ladder_cases():
+    data = helpers.golden('csc_ladder_cases.npz')
+    return [helpers.Case(data, str(n)) for n in data['names']]
+
+
+@pytest.mark.parametrize('case', [c for c in _csc_ladder_cases() if c.n <= 12 or 'hubbard' in c.name],
+                         ids=lambda c: c.name)
+def test_oracle_csc_matches_reference_hashes(case):
+    """CSC ladder (tests/golden/csc_ladder_cases.npz): the scipy-based oracle against sha256 of the
+    real reference's matrices.  The 14-qubit molecular cases need gigabytes of triplets, as in the
+    reference, and are left to the GPU suite."""
+    import hashlib
+
+    def sha(a):
+        return hashlib.sha256(numpy.ascontiguousarray(a).tobytes()).hexdigest()
+    if str(case['route']) == 'pauli':
+        mat = po.qubit_operator_sparse(helpers.qubit_case_operator(case).terms, case.n)
+    else:
+        op = helpers.fermion_operator_from(case['terms'], case['coeffs'], case['coeff_is_complex'])
+        mat = po.jordan_wigner_sparse(op.terms, case.n)
+    assert mat.nnz == int(case['nnz']) and str(mat.indices.dtype) == str(case['index_dtype'])
+    assert sha(mat.indptr) == str(case['indptr_sha256'])
+    assert sha(mat.indices) == str(case['indices_sha256'])
+    assert sha(mat.data) == str(case['data_sha256'])
+
+
 def test_ground_state_known_answer():
     # sparse_tools_test.py:593-604
     op = QubitOperator('Y0 X1') + QubitOperator('Z0 Z1')
