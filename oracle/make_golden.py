@@ -499,6 +499,58 @@ def csc_ladder_cases():
     print('csc_ladder_cases:', len(names), 'cases')
 
 
+def energy_ladder_cases():
+    """Eigenvalue ladder (ground state by the CSC route and matrix-free up
+    to n = 16, Davidson at n = 12): the reference's own get_ground_state / get_gap /
+    jw_get_ground_state_at_particle_number / QubitDavidson results.  Spectra are degenerate:
+    only energies are stored."""
+    import time
+    from openfermion.linalg import (QubitDavidson, get_gap, jw_get_ground_state_at_particle_number,
+                                    variance)
+    cases = {}
+    names = []
+    ops = {
+        'hubbard_2x4_n16': (jordan_wigner(fermi_hubbard(2, 4, 1.0, 4.0)), 16, (2, 4, 8)),
+        'hubbard_2x3_mu_h_n12': (jordan_wigner(fermi_hubbard(2, 3, 1.0, 4.0, 0.3, 0.2)), 12, (3, 6)),
+        'molecular_6_n12': (jordan_wigner(random_interaction_operator(6, expand_spin=True, real=True, seed=7)), 12, (2, 6)),
+        'molecular_7_n14': (jordan_wigner(random_interaction_operator(7, expand_spin=True, real=True, seed=1234)), 14, (4,)),
+    }
+    for name, (op, n, numbers) in ops.items():
+        t0 = time.time()
+        mat = get_sparse_operator(op, n)
+        e0, state = get_ground_state(mat)
+        gap = get_gap(mat)
+        e0_linear = None
+        if n <= 12:  # matrix-free ARPACK through the reference's LinearQubitOperator: slow
+            e0_linear, _ = get_ground_state(LinearQubitOperator(op, n))
+        strs, coeffs, is_complex = pack_terms(op.terms, qubit_term_str)
+        cases[name + '/terms'] = strs
+        cases[name + '/coeffs'] = coeffs
+        cases[name + '/coeff_is_complex'] = is_complex
+        cases[name + '/n_qubits'] = numpy.array(n)
+        cases[name + '/e0'] = numpy.array(e0)
+        cases[name + '/gap'] = numpy.array(gap)
+        cases[name + '/variance_of_ground_state'] = numpy.array(variance(mat, state))
+        if e0_linear is not None:
+            cases[name + '/e0_matrix_free'] = numpy.array(e0_linear)
+        cases[name + '/particle_numbers'] = numpy.array(numbers)
+        cases[name + '/e0_at_particle_number'] = numpy.array(
+            [jw_get_ground_state_at_particle_number(mat, k)[0] for k in numbers])
+        if n == 12:  # the reference's Davidson test size (davidson_test.py)
+            import copy
+            real_op = copy.deepcopy(op)
+            real_op.compress()  # complex-typed coefficients make the reference's diagonal raise
+            numpy.random.seed(7)
+            success, values, _ = QubitDavidson(real_op, n).get_lowest_n(2, max_iterations=60)
+            cases[name + '/davidson_success'] = numpy.array(bool(success))
+            cases[name + '/davidson_lowest2'] = numpy.array(values)
+        names.append(name)
+        print('  %s: E0 = %.12f gap = %.3e  (%.1f s)' % (name, e0, gap, time.time() - t0))
+    cases['names'] = numpy.array(names, dtype=str)
+    numpy.savez_compressed(os.path.join(GOLDEN, 'energy_ladder_cases.npz'), **cases)
+    print('energy_ladder_cases:', len(names), 'cases')
+
+
 if __name__ == '__main__':
     os.makedirs(GOLDEN, exist_ok=True)
     which = sys.argv[1:] or ['qubit', 'fermion', 'lih', 'sector', 'files', 'ladder']
@@ -506,6 +558,8 @@ if __name__ == '__main__':
         ladder_cases()
     if 'large' in which:  # minutes of reference time: not part of the default set
         large_cases()
+    if 'energy_ladder' in which:
+        energy_ladder_cases()
     if 'csc_ladder' in which:  # gigabytes of triplets in the reference: not part of the default set
         csc_ladder_cases()
     if 'qubit' in which:
