@@ -1,0 +1,31 @@
+#!/bin/bash
+# Measurements that were prepared on CPU after the round-1 GPU budget was spent; run each block
+# under gpurun with the stated GPU count (see DESIGN.md section 4 K6 "Qubit order inside a shard").
+#
+#   gpurun --timeout 300 -- 'bash scripts/pending_measurements.sh one'
+#   gpurun --gpus 2 --timeout 200 -- 'bash scripts/pending_measurements.sh multi 2'
+#   gpurun --gpus 8 --timeout 300 -- 'bash scripts/pending_measurements.sh multi 8'
+set -u
+mkdir -p gpurun_out
+case "${1:-one}" in
+one)
+    # the whole GPU suite (includes the reference-ladder file added after the last GPU run)
+    python -m pytest tests -m gpu -x -q > gpurun_out/pytest_gpu_pending.log 2>&1
+    tail -3 gpurun_out/pytest_gpu_pending.log
+    ;;
+multi)
+    N="${2:-2}"
+    # correctness of every basis / exchange combination, then the 32-qubit Hubbard H|psi> with
+    # top-qubit shards, parity shards, and parity shards + locality-ordered local qubits
+    OFB_DIST_QUICK=1 OFB_DIST_BENCH_QUBITS=32 timeout 200 python -m torch.distributed.run --nnodes=1 \
+        --nproc-per-node "$N" --master-addr 127.0.0.1 --master-port 29531 tests/dist_gpu_check.py \
+        > "gpurun_out/dist_check${N}_locality.log" 2>&1
+    tail -8 "gpurun_out/dist_check${N}_locality.log"
+    # config 5 (32-qubit Lanczos ground state) in the new basis
+    if [ "$N" = 8 ]; then
+        timeout 200 python -m torch.distributed.run --nnodes=1 --nproc-per-node 8 --master-addr 127.0.0.1 \
+            --master-port 29532 scripts/run_config5.py > gpurun_out/config5_n32_8gpu_symmetry.log 2>&1
+        tail -2 gpurun_out/config5_n32_8gpu_symmetry.log
+    fi
+    ;;
+esac
