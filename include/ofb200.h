@@ -114,6 +114,18 @@ int ofb_apply_groups(ofb_plan *plan, const void *d_in, void *d_out, int local_bi
                      uint64_t index_base, int64_t g_begin, int64_t g_end, int accumulate,
                      void *stream);
 
+/* Optional "support" hints for K1/K2 (experimental, off unless set): for group g the caller
+ * asserts  S_g(j) == 0  unless  parity(j & mask1[g]) == (flags[g] >> 1 & 1)  [if flags[g] & 1]
+ *                       and     parity(j & mask2[g]) == (flags[g] >> 3 & 1)  [if flags[g] & 4],
+ * j being the global basis index.  Number- and spin-conserving Hamiltonians have such masks for
+ * every x != 0 group (a hop X_a X_b + Y_a Y_b only connects states with bit a != bit b); the
+ * kernel then skips the gathers of amplitudes whose coefficient is structurally zero (half of
+ * them for a hopping group, three quarters for a mixed-spin double excitation).  The hints are
+ * trusted: wrong hints give wrong results.  openfermion_b200/support.py derives them from the
+ * term table.  n_qubits <= 32 only.  n_groups must equal the plan's group count. */
+int ofb_plan_set_support(ofb_plan *plan, int64_t n_groups, const uint32_t *mask1,
+                         const uint32_t *mask2, const uint8_t *flags);
+
 /* Host-buffer convenience: H2D, ofb_apply, D2H (the call LinearQubitOperator.matvec makes).
  * h_in/h_out are column-contiguous complex128 arrays of 2^n * ncols elements. */
 int ofb_apply_host(ofb_plan *plan, const void *h_in, void *h_out, int ncols);

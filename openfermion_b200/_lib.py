@@ -55,6 +55,7 @@ SIGNATURES = {
     'ofb_plan_create_projected': (c_int, [c_int, c_int64, c_void_p, c_void_p, c_void_p, c_void_p,
                                           c_void_p, c_int, P(c_void_p)]),
     'ofb_plan_destroy': (c_int, [c_void_p]),
+    'ofb_plan_set_support': (c_int, [c_void_p, c_int64, c_void_p, c_void_p, c_void_p]),
     'ofb_plan_info': (c_int, [c_void_p, P(c_int), P(c_int64), P(c_int64), P(c_int64), P(c_int)]),
     'ofb_plan_group': (c_int, [c_void_p, c_int64, P(c_uint64), P(c_int64)]),
     'ofb_apply': (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int64, c_void_p]),

@@ -161,6 +161,17 @@ __device__ __forceinline__ void load_tile(const double2 *__restrict__ vin, uint3
     for (int r = 0; r < RT; ++r) v[r] = vin[(size_t)(jx ^ (uint32_t)(r << CLASS_SHIFT))];
 }
 
+// Same with a support hint (ofb_plan_set_support): amplitudes whose coefficient S_g(j) is
+// structurally zero are not fetched; they enter the sums as exact zeros.
+__device__ __forceinline__ void load_tile_needed(const double2 *__restrict__ vin, uint32_t jx,
+                                                 uint32_t need, double2 (&v)[RT]) {
+#pragma unroll
+    for (int r = 0; r < RT; ++r) {
+        v[r] = make_double2(0.0, 0.0);
+        if ((need >> r) & 1u) v[r] = vin[(size_t)(jx ^ (uint32_t)(r << CLASS_SHIFT))];
+    }
+}
+
 // Shared-memory stage of one chunk: segment descriptors and both coefficient tables.
 struct StageBuf {
     Segment segs[CHUNK_MAX_SEGS];
@@ -178,10 +189,14 @@ __device__ __forceinline__ void cp_async_wait() {
     asm volatile("cp.async.wait_group %0;\n" ::"n"(N) : "memory");
 }
 
-__device__ __forceinline__ void stage_chunk(StageBuf &b, const Chunk ck,
+template <bool COND>
+__device__ __forceinline__ void stage_chunk(StageBuf &b, SegCond *sc, const Chunk ck,
                                             const Segment *__restrict__ segs,
+                                            const SegCond *__restrict__ conds,
                                             const TermZC *__restrict__ zc_re,
                                             const TermZC *__restrict__ zc_im, int has_imag) {
+    if (COND)
+        for (uint32_t u = threadIdx.x; u < ck.seg_count; u += BLOCK) cp_async16(sc + u, conds + ck.seg_begin + u);
     const char *gs = (const char *)(segs + ck.seg_begin);
     char *ss = (char *)b.segs;
     for (uint32_t u = threadIdx.x; u < ck.seg_count * 2; u += BLOCK) cp_async16(ss + u * 16, gs + u * 16);
@@ -192,14 +207,16 @@ __device__ __forceinline__ void stage_chunk(StageBuf &b, const Chunk ck,
     cp_async_commit();
 }
 
-template <bool Z32, bool EXPECT, bool HAS_IMAG>
+template <bool Z32, bool EXPECT, bool HAS_IMAG, bool COND>
 __global__ void __launch_bounds__(BLOCK, OFB_APPLY_MIN_CTAS)
 k_apply_tile(const double2 *__restrict__ vin, double2 *__restrict__ vout,
          const Chunk *__restrict__ chunks, uint32_t c0, uint32_t c1,
          const Segment *__restrict__ segs, uint32_t s0, uint32_t s1,
          const TermZC *__restrict__ zc_re, const TermZC *__restrict__ zc_im, int has_imag,
-         uint32_t xmask_local, uint64_t index_base, int accumulate, double2 *__restrict__ partials) {
+         uint32_t xmask_local, uint64_t index_base, int accumulate, double2 *__restrict__ partials,
+         const SegCond *__restrict__ conds) {
     __shared__ StageBuf sbuf[2];
+    __shared__ SegCond scond[COND ? 2 : 1][COND ? CHUNK_MAX_SEGS : 1];
     const uint32_t j0 = blockIdx.x * (uint32_t)TILE + threadIdx.x;  // local index of r = 0
     const uint32_t j_lo = (uint32_t)index_base | j0;
     const uint32_t base_hi = (uint32_t)(index_base >> 32);
@@ -221,11 +238,12 @@ k_apply_tile(const double2 *__restrict__ vin, double2 *__restrict__ vout,
 
     Chunk cur = chunks[c0];
     Chunk nxt = (c0 + 1 < c1) ? chunks[c0 + 1] : cur;
-    stage_chunk(sbuf[0], cur, segs, zc_re, zc_im, HAS_IMAG ? 1 : 0);
+    stage_chunk<COND>(sbuf[0], scond[0], cur, segs, conds, zc_re, zc_im, HAS_IMAG ? 1 : 0);
     for (uint32_t c = c0; c < c1; ++c) {
         Chunk after = nxt;
         if (c + 1 < c1) {
-            stage_chunk(sbuf[(c + 1 - c0) & 1], nxt, segs, zc_re, zc_im, HAS_IMAG ? 1 : 0);
+            stage_chunk<COND>(sbuf[(c + 1 - c0) & 1], scond[COND ? ((c + 1 - c0) & 1) : 0], nxt, segs, conds,
+                              zc_re, zc_im, HAS_IMAG ? 1 : 0);
             if (c + 2 < c1) after = chunks[c + 2];
             cp_async_wait<1>();
         } else {
@@ -243,7 +261,17 @@ k_apply_tile(const double2 *__restrict__ vin, double2 *__restrict__ vout,
             const uint32_t jx = j0 ^ (sd.x_lo & xmask_local);
             const uint32_t runs = kind_runs & 0xfu;
             double2 v[RT];
-            load_tile(vin, jx, v);
+            if (COND) {
+                // which of this thread's amplitudes can have a non-zero coefficient in this group
+                const SegCond cd = scond[(c - c0) & 1][s - cur.seg_begin];
+                const uint32_t q1 = ((uint32_t)__popc(j_lo & cd.m1) + cd.v) & 1u;
+                const uint32_t q2 = ((uint32_t)__popc(j_lo & cd.m2) + (cd.v >> 1)) & 1u;
+                const uint32_t need = (cd.pat ^ (q1 - 1u)) & ((cd.pat >> 16) ^ (q2 - 1u)) & ((1u << RT) - 1u);
+                if (need == 0u) continue;
+                load_tile_needed(vin, jx, need, v);
+            } else {
+                load_tile(vin, jx, v);
+            }
             if (!HAS_IMAG) {
                 segment_pass<Z32, false>(b.re + tl, runs, cnts, ids, j_lo, base_hi, v, ar, ai);
             } else {
@@ -400,14 +428,16 @@ static int launch_apply_impl(ofb_plan *p, const void *d_in, void *d_out, int loc
     double2 *out = (double2 *)d_out;
     if (local_bits >= TILE_BITS) {
         const uint32_t xmask = (uint32_t)(dim - 1);
-#define OFB_GO(ZZ, II)                                                                         \
-    k_apply_tile<ZZ, EXPECT, II><<<(unsigned)blocks, BLOCK, 0, s>>>(                               \
+#define OFB_GO(ZZ, II, CC)                                                                     \
+    k_apply_tile<ZZ, EXPECT, II, CC><<<(unsigned)blocks, BLOCK, 0, s>>>(                           \
         in, out, p->d_chunks, c0, c1, p->d_segs, s0, s1, p->d_zc, p->d_zc_im, 0, xmask,        \
-        index_base, accumulate, partials)
-        if (p->z_fits32) {
-            if (p->has_imag) OFB_GO(true, true); else OFB_GO(true, false);
+        index_base, accumulate, partials, p->d_conds)
+        if (p->z_fits32 && p->has_cond) {  // support hints (ofb_plan_set_support), n <= 32 only
+            if (p->has_imag) OFB_GO(true, true, true); else OFB_GO(true, false, true);
+        } else if (p->z_fits32) {
+            if (p->has_imag) OFB_GO(true, true, false); else OFB_GO(true, false, false);
         } else {
-            if (p->has_imag) OFB_GO(false, true); else OFB_GO(false, false);
+            if (p->has_imag) OFB_GO(false, true, false); else OFB_GO(false, false, false);
         }
 #undef OFB_GO
     } else {

@@ -89,6 +89,16 @@ struct __align__(16) Chunk {
     uint32_t seg_begin, seg_count;
     uint32_t term_begin, term_count;
 };
+// Optional support hint of a segment's group (ofb_plan_set_support): amplitude r of a thread
+// whose r = 0 amplitude has global index j needs the group only if
+//   parity(r & w_k) == v_k ^ parity(j & m_k)   for k = 1, 2,   w_k = (m_k >> CLASS_SHIFT) & CLASS_MASK.
+// `pat` holds the two 16-bit patterns {r : parity(r & w_k) = 1} (low half k = 1), `v` bit k-1 = v_k.
+// A missing condition is stored as m = 0, v = 1, pattern 0xffff (always needed).
+struct __align__(16) SegCond {
+    uint32_t m1, m2;
+    uint32_t pat;
+    uint32_t v;
+};
 // One component (real or imaginary part) of c_t = coeff_t * (-i)^y_t next to the z mask, so
 // that one 128-bit warp-uniform load fetches both.
 struct __align__(16) TermZC {
@@ -130,6 +140,8 @@ struct ofb_plan {
     ofb::TermZC *d_zc = nullptr;     // (z, Re c) in segment/class order
     ofb::TermZC *d_zc_im = nullptr;  // (z, Im c) in the same order
     ofb::GroupDesc *d_groups = nullptr;  // scatter-form groups (CSC)
+    ofb::SegCond *d_conds = nullptr;     // per segment, only after ofb_plan_set_support
+    bool has_cond = false;
     // device tables: scatter form (CSC)
     ofb::ScatterRow *d_rows = nullptr;       // grouped by x (stable), for the fast CSC mode
     ofb::ScatterRow *d_rows_orig = nullptr;  // caller's term order, for the scipy-order mode

@@ -472,6 +472,7 @@ int ofb_plan_destroy(ofb_plan *p) {
     if (!p) return OFB_OK;
     cudaSetDevice(p->device);
     cudaFree(p->d_groups);
+    cudaFree(p->d_conds);
     cudaFree(p->d_segs);
     cudaFree(p->d_seg_term_begin);
     cudaFree(p->d_chunks);
@@ -490,6 +491,54 @@ int ofb_plan_destroy(ofb_plan *p) {
     cudaGetLastError();
     delete p;
     return OFB_OK;
+}
+
+int ofb_plan_set_support(ofb_plan *p, int64_t n_groups, const uint32_t *mask1, const uint32_t *mask2,
+                         const uint8_t *flags) {
+    if (!p) return fail(OFB_ERR_INVALID, "plan is NULL");
+    if (p->projected) return fail(OFB_ERR_INVALID, "projected plans support only csc_* calls");
+    if (n_groups != p->n_groups) return fail(OFB_ERR_INVALID, "n_groups differs from the plan's group count");
+    if (n_groups > 0 && (!mask1 || !mask2 || !flags)) return fail(OFB_ERR_INVALID, "NULL argument");
+    if (p->n_qubits > 32) return fail(OFB_ERR_INVALID, "support hints need n_qubits <= 32");
+    OFB_TRY
+    OFB_CUDA(cudaSetDevice(p->device));
+    cudaFree(p->d_conds);
+    p->d_conds = nullptr;
+    p->has_cond = false;
+    auto pattern = [](uint32_t m) {  // {r : parity(r & w) = 1} for the class bits of m
+        const uint32_t w = (m >> CLASS_SHIFT) & CLASS_MASK;
+        uint32_t pat = 0;
+        for (uint32_t r = 0; r < (1u << CLASS_BITS); ++r)
+            if (__builtin_popcount(r & w) & 1) pat |= 1u << r;
+        return pat;
+    };
+    const uint32_t all = (1u << (1u << CLASS_BITS)) - 1u;  // 16 (or 8) amplitudes per thread
+    const size_t n_segs = p->h_seg_begin.empty() ? 0 : p->h_seg_begin[p->n_groups];
+    std::vector<SegCond> conds(n_segs);
+    bool any = false;
+    for (int64_t g = 0; g < n_groups; ++g) {
+        SegCond cd{0u, 0u, all | (all << 16), 3u};
+        if (flags[g] & 1) {
+            cd.m1 = mask1[g];
+            cd.pat = (cd.pat & 0xffff0000u) | pattern(mask1[g]);
+            cd.v = (cd.v & ~1u) | ((flags[g] >> 1) & 1u);
+            any = true;
+        }
+        if (flags[g] & 4) {
+            cd.m2 = mask2[g];
+            cd.pat = (cd.pat & 0x0000ffffu) | (pattern(mask2[g]) << 16);
+            cd.v = (cd.v & ~2u) | (((flags[g] >> 3) & 1u) << 1);
+            any = true;
+        }
+        for (uint32_t sidx = p->h_seg_begin[g]; sidx < p->h_seg_begin[g + 1]; ++sidx) conds[sidx] = cd;
+    }
+    if (any) {
+        int rc = upload(&p->d_conds, conds);
+        if (rc) return rc;
+        p->has_cond = true;
+    }
+    return OFB_OK;
+    OFB_CATCH((void)0)
 }
 
 int ofb_plan_set_csc_mode(ofb_plan *p, int mode) {

@@ -1,5 +1,6 @@
 """Python owner of an `ofb_plan` (compiled term tables on one GPU)."""
 import ctypes
+import os
 
 import numpy
 import scipy.sparse
@@ -27,6 +28,9 @@ class PauliPlan:
         self.device = device
         self.projected = False
         self._read_info()
+        self.support_fraction = 1.0
+        if os.environ.get('OFB_SUPPORT_HINTS') == '1' and self.n_qubits <= 32 and len(c):
+            self.set_support_hints(x, z, c)
 
     @classmethod
     def projected_rows(cls, n_qubits, occ_mask, occ_val, x_mask, z_mask, coeff, device=0):
@@ -54,6 +58,20 @@ class PauliPlan:
         _lib.call('ofb_plan_info', self.handle, ctypes.byref(n), ctypes.byref(t), ctypes.byref(g),
                   ctypes.byref(d), ctypes.byref(dev))
         self.n_terms, self.n_groups, self.n_diag_terms = t.value, g.value, d.value
+
+    def set_support_hints(self, x_mask, z_mask, coeff):
+        """Experimental (openfermion_b200/support.py): tell the kernels where each group's
+        coefficient is structurally zero, so that those gathers are skipped."""
+        from openfermion_b200 import support
+        group_x, mask1, mask2, flags = support.group_conditions(x_mask, z_mask, coeff)
+        if len(group_x) != self.n_groups:
+            raise ValueError('support hints were derived for a different term table')
+        m1 = numpy.ascontiguousarray(mask1, dtype=numpy.uint32)
+        m2 = numpy.ascontiguousarray(mask2, dtype=numpy.uint32)
+        flags = numpy.ascontiguousarray(flags, dtype=numpy.uint8)
+        _lib.call('ofb_plan_set_support', self.handle, c_int64(self.n_groups), _lib.ptr(m1), _lib.ptr(m2),
+                  _lib.ptr(flags))
+        self.support_fraction = support.needed_fraction(flags)
 
     def group(self, g):
         x = ctypes.c_uint64()

@@ -1,0 +1,117 @@
+"""Support hints for the matrix-free kernels: where an x-group's coefficient vanishes.
+
+In the gather form  out[j] = sum_g S_g(j) in[j ^ x_g],  S_g(j) = sum_{t in g} k_t (-1)^{|j & z_t|}
+(k_t = coeff_t (-i)^{|x & z_t|}), the coefficient S_g(j) of a symmetric Hamiltonian is zero on
+most of the index space: a hopping group X_a X_b + Y_a Y_b (both with the same Z string) only
+connects basis states whose bits a and b differ, a double excitation only states with the right
+occupation pattern.  The reference never notices (it applies term by term,
+linalg/linear_qubit_operator.py:107-148); a kernel that gathers in[j ^ x] for every j fetches
+two to four times more amplitudes than contribute.
+
+Algebra.  If the term set of a group is invariant under  z -> z ^ m,  k -> s k  (s = +-1), then
+chi_m(j) S_g(j) = s S_g(j)  with  chi_m(j) = (-1)^{|j & m|},  so
+
+    S_g(j) = 0   unless   parity(j & m) == (1 if s == -1 else 0).
+
+`group_conditions` finds up to two independent such (m, s) per group directly from the term
+table -- no knowledge of spin or particle number is needed, and encodings other than
+Jordan-Wigner simply yield whatever symmetry their strings have.  The conditions go to the
+library with `ofb_plan_set_support` (include/ofb200.h); the kernel then skips the gathers, and
+whole warps skip groups whose condition does not depend on the lane or class bits.
+
+Experimental in round 1: derived and tested on the CPU, kernel variant compiled, NOT yet run on
+a GPU; off unless OFB_SUPPORT_HINTS=1.
+"""
+import numpy
+
+# relative tolerance on "equal coefficients": the strings of one fermionic excitation get their
+# coefficients from the same integrals but possibly through differently ordered sums
+COEFF_RTOL = 8 * numpy.finfo(numpy.float64).eps
+
+
+def _phased(x, z, c):
+    """Gather-form coefficients k_t = c_t (-i)^{|x & z_t|} (what the kernels sum)."""
+    y = numpy.bitwise_count(numpy.asarray(x, dtype=numpy.uint64) & numpy.asarray(z, dtype=numpy.uint64))
+    return numpy.asarray(c, dtype=numpy.complex128) * numpy.array([1, -1j, -1, 1j])[y % 4]
+
+
+def _group_symmetries(zs, ks):
+    """All (m, v) with S(j) = 0 unless parity(j & m) == v, for one group (python ints / complex)."""
+    if len(zs) < 2:
+        return []
+    index = {}
+    for t, zt in enumerate(zs):
+        if zt in index:  # the same string twice: merge first (cannot happen for canonical operators)
+            return []
+        index[zt] = t
+    scale = max(abs(k) for k in ks)
+    if scale == 0.0:
+        return []
+    tol = COEFF_RTOL * scale
+    found = []
+    for t in range(1, len(zs)):
+        m = zs[0] ^ zs[t]
+        for s in (1.0, -1.0):
+            if abs(ks[t] - s * ks[0]) > tol:
+                continue
+            ok = True
+            for u, zu in enumerate(zs):
+                w = index.get(zu ^ m)
+                if w is None or abs(ks[w] - s * ks[u]) > tol:
+                    ok = False
+                    break
+            if ok:
+                found.append((m, 0 if s > 0 else 1))
+                break
+    return found
+
+
+def _cost(m, low_bits=10):
+    """Prefer masks that do not touch the lane / class bits (whole warps can skip the group) and,
+    among those that do, masks that leave bit 0 alone (32-byte sectors hold two amplitudes)."""
+    return (bin(m & ((1 << low_bits) - 1)).count('1'), m & 1, m)
+
+
+def group_conditions(x, z, c):
+    """Per x-group (ascending x = the plan's group order): up to two independent conditions.
+
+    Returns (group_x u64[G], mask1 u64[G], mask2 u64[G], flags u8[G]) with
+    flags bit0: condition 1 present, bit1: its parity value v1, bit2 / bit3 likewise for 2."""
+    x = numpy.asarray(x, dtype=numpy.uint64)
+    z = numpy.asarray(z, dtype=numpy.uint64)
+    k = _phased(x, z, c)
+    order = numpy.argsort(x, kind='stable')
+    xs = x[order]
+    group_x, starts = numpy.unique(xs, return_index=True)
+    bounds = list(starts) + [len(xs)]
+    n_groups = len(group_x)
+    mask1 = numpy.zeros(n_groups, dtype=numpy.uint64)
+    mask2 = numpy.zeros(n_groups, dtype=numpy.uint64)
+    flags = numpy.zeros(n_groups, dtype=numpy.uint8)
+    z_list = z[order].tolist()
+    k_list = k[order].tolist()
+    for g in range(n_groups):
+        b, e = bounds[g], bounds[g + 1]
+        if int(group_x[g]) == 0:
+            continue  # the diagonal group: no gather to skip
+        sym = sorted(_group_symmetries(z_list[b:e], k_list[b:e]), key=lambda mv: _cost(mv[0]))
+        if not sym:
+            continue
+        (m1, v1) = sym[0]
+        mask1[g] = m1
+        flags[g] |= 1 | (v1 << 1)
+        for m2, v2 in sym[1:]:
+            if m2 != m1:  # two distinct non-zero vectors over GF(2) are independent
+                mask2[g] = m2
+                flags[g] |= 4 | (v2 << 3)
+                break
+    return group_x, mask1, mask2, flags
+
+
+def needed_fraction(flags):
+    """Share of (group, amplitude) gathers that remain: 1/2 per condition."""
+    flags = numpy.asarray(flags)
+    if len(flags) == 0:
+        return 1.0
+    per_group = 0.5 ** ((flags & 1) + ((flags >> 2) & 1)).astype(float)
+    return float(per_group.mean())

@@ -3,6 +3,7 @@
 # under gpurun with the stated GPU count (see DESIGN.md section 4 K6 "Qubit order inside a shard").
 #
 #   gpurun --timeout 300 -- 'bash scripts/pending_measurements.sh one'
+#   gpurun --timeout 300 -- 'bash scripts/pending_measurements.sh hints'
 #   gpurun --gpus 2 --timeout 200 -- 'bash scripts/pending_measurements.sh multi 2'
 #   gpurun --gpus 8 --timeout 300 -- 'bash scripts/pending_measurements.sh multi 8'
 set -u
@@ -12,6 +13,14 @@ one)
     # the whole GPU suite (includes the reference-ladder file added after the last GPU run)
     python -m pytest tests -m gpu -x -q > gpurun_out/pytest_gpu_pending.log 2>&1
     tail -3 gpurun_out/pytest_gpu_pending.log
+    ;;
+hints)
+    # experimental support-hint kernel (openfermion_b200/support.py): correctness, then timing
+    OFB_TEST_EXPERIMENTAL=1 python -m pytest tests/test_gpu_support_hints.py -m gpu -x -q 2>&1 | tail -3
+    for w in hub30 mol26; do
+        python scripts/quick_apply_bench.py $w
+        OFB_SUPPORT_HINTS=1 python scripts/quick_apply_bench.py $w
+    done
     ;;
 multi)
     N="${2:-2}"

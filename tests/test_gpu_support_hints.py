@@ -1,0 +1,84 @@
+"""EXPERIMENTAL (not run by default): the support-hint kernel variant
+(k_apply_tile<..., COND = true>, ofb_plan_set_support, openfermion_b200/support.py) was written
+after the round-1 GPU budget was spent and has never run on a GPU.  Enable with
+OFB_TEST_EXPERIMENTAL=1:   OFB_TEST_EXPERIMENTAL=1 python -m pytest tests/test_gpu_support_hints.py -m gpu
+The checks: same H|psi>, expectation and sharded partial applies with and without hints."""
+import os
+
+import numpy
+import pytest
+
+import helpers
+from openfermion_b200 import compiler, hamiltonians
+
+pytestmark = [pytest.mark.gpu,
+              pytest.mark.skipif(os.environ.get('OFB_TEST_EXPERIMENTAL') != '1',
+                                 reason='experimental kernel variant, set OFB_TEST_EXPERIMENTAL=1')]
+
+CASES = [
+    ('hubbard_2x4_n16', lambda: hamiltonians.hubbard_jw(2, 4), 16),
+    ('hubbard_2x5_mu_h_n20', lambda: hamiltonians.hubbard_jw(2, 5, 1.0, 4.0, 0.3, 0.2), 20),
+    ('hubbard_2x4_bk_n16', lambda: hamiltonians.hubbard_jw(2, 4, encoding='bk'), 16),
+    ('molecular_n12', lambda: hamiltonians.molecular_jw(6, seed=1234), 12),
+    ('molecular_n16', lambda: hamiltonians.molecular_jw(8, seed=1234), 16),
+    ('molecular_bk_n14', lambda: hamiltonians.molecular_jw(7, seed=5, encoding='bk'), 14),
+    ('complex_paulis_n13', lambda: hamiltonians.random_pauli_sum(13, 200, 2, True), 13),
+]
+
+
+def _state(n, seed):
+    rng = numpy.random.default_rng(seed)
+    v = rng.normal(size=2**n) + 1j * rng.normal(size=2**n)
+    return v / numpy.linalg.norm(v)
+
+
+@pytest.mark.parametrize('name,builder,n', CASES, ids=[c[0] for c in CASES])
+def test_hints_do_not_change_the_result(name, builder, n):
+    from openfermion_b200.plan import PauliPlan
+    op = builder()
+    x, z, c = compiler.compile_qubit_operator(op, n)
+    plain = PauliPlan(n, x, z, c)
+    hinted = PauliPlan(n, x, z, c)
+    hinted.set_support_hints(x, z, c)
+    v = _state(n, 3)
+    want = plain.apply_host(v)
+    got = hinted.apply_host(v)
+    assert helpers.close(got, want, 1e-13)
+    assert abs(hinted.expectation_host(v) - plain.expectation_host(v)) <= 1e-12 * numpy.sum(numpy.abs(c))
+    if 'hubbard' in name or 'molecular' in name:
+        assert hinted.support_fraction < 0.6
+
+
+def test_hints_with_shards_and_accumulate():
+    """index_base bits take part in the parity of a condition: virtual ranks on one GPU."""
+    from openfermion_b200 import _lib
+    from openfermion_b200.distributed import ShardLayout
+    from openfermion_b200.linalg import krylov
+    from openfermion_b200.plan import PauliPlan
+    from openfermion_b200.shard_basis import ShardBasis
+    n, world = 16, 8
+    op = hamiltonians.hubbard_jw(2, 4)
+    x, z, c = compiler.compile_qubit_operator(op, n)
+    for kind in ('natural', 'symmetry'):
+        basis = ShardBasis.natural(n) if kind == 'natural' else \
+            ShardBasis.for_sharding(n, 3, x, local_order='locality')
+        xb, zb, cb = basis.transform_terms(x, z, c)
+        plain = PauliPlan(n, xb, zb, cb)
+        hinted = PauliPlan(n, xb, zb, cb)
+        hinted.set_support_hints(xb, zb, cb)
+        layout = ShardLayout(n, world, xb)
+        v = basis.from_natural(_state(n, 5))
+        d_in = _lib.to_device(v)
+        outs = []
+        for plan in (plain, hinted):
+            d_out = _lib.DeviceBuffer(v.nbytes)
+            ld = layout.local_dim
+            for rank in range(world):
+                first = True
+                for x_hi, g0, g1 in layout.patterns:
+                    src = d_in.ptr + layout.peer(rank, x_hi) * ld * 16
+                    plan.apply_groups_device(src, d_out.ptr + rank * ld * 16, layout.local_bits,
+                                             layout.index_base(rank), g0, g1, 0 if first else 1)
+                    first = False
+            outs.append(krylov.download(1 << n, d_out.ptr))
+        assert helpers.close(outs[1], outs[0], 1e-13)
