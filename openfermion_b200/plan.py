@@ -29,8 +29,10 @@ class PauliPlan:
         self.projected = False
         self._read_info()
         self.support_fraction = 1.0
-        if os.environ.get('OFB_SUPPORT_HINTS') == '1' and self.n_qubits <= 32 and len(c):
-            self.set_support_hints(x, z, c)
+        self._k1_handle = None  # separate plan of the reduced term table (support hints)
+        mode = os.environ.get('OFB_SUPPORT_HINTS')  # experimental: '1' = hints + reduced table, 'hints'
+        if mode in ('1', 'hints') and self.n_qubits <= 32 and len(c):
+            self.set_support_hints(x, z, c, reduce=(mode == '1'))
 
     @classmethod
     def projected_rows(cls, n_qubits, occ_mask, occ_val, x_mask, z_mask, coeff, device=0):
@@ -59,9 +61,11 @@ class PauliPlan:
                   ctypes.byref(d), ctypes.byref(dev))
         self.n_terms, self.n_groups, self.n_diag_terms = t.value, g.value, d.value
 
-    def set_support_hints(self, x_mask, z_mask, coeff):
+    def set_support_hints(self, x_mask, z_mask, coeff, reduce=True):
         """Experimental (openfermion_b200/support.py): tell the kernels where each group's
-        coefficient is structurally zero, so that those gathers are skipped."""
+        coefficient is structurally zero, so that those gathers are skipped; with reduce=True
+        K1/K2 also run on the orbit-reduced term table (one term per symmetry orbit), held in
+        a second library plan -- diagonal and CSC keep the full table."""
         from openfermion_b200 import support
         group_x, mask1, mask2, flags = support.group_conditions(x_mask, z_mask, coeff)
         if len(group_x) != self.n_groups:
@@ -69,9 +73,29 @@ class PauliPlan:
         m1 = numpy.ascontiguousarray(mask1, dtype=numpy.uint32)
         m2 = numpy.ascontiguousarray(mask2, dtype=numpy.uint32)
         flags = numpy.ascontiguousarray(flags, dtype=numpy.uint8)
-        _lib.call('ofb_plan_set_support', self.handle, c_int64(self.n_groups), _lib.ptr(m1), _lib.ptr(m2),
+        target = self.handle
+        if reduce and numpy.any(flags):
+            xr, zr, cr = support.reduce_terms(x_mask, z_mask, coeff, group_x, mask1, mask2, flags)
+            xr, zr, cr = (numpy.ascontiguousarray(a) for a in (xr, zr, cr))
+            self._drop_k1()
+            handle = c_void_p()
+            _lib.call('ofb_plan_create', c_int(self.n_qubits), c_int64(len(xr)), _lib.ptr(xr), _lib.ptr(zr),
+                      _lib.ptr(cr), c_int(self.device), ctypes.byref(handle))
+            self._k1_handle = target = handle
+            self.n_reduced_terms = len(xr)
+        _lib.call('ofb_plan_set_support', target, c_int64(self.n_groups), _lib.ptr(m1), _lib.ptr(m2),
                   _lib.ptr(flags))
         self.support_fraction = support.needed_fraction(flags)
+
+    def _drop_k1(self):
+        if getattr(self, '_k1_handle', None):
+            _lib.call('ofb_plan_destroy', self._k1_handle)
+            self._k1_handle = None
+
+    @property
+    def _apply_handle(self):
+        """The plan K1 / K2 run on: the reduced one when support hints are active."""
+        return getattr(self, '_k1_handle', None) or self.handle
 
     def group(self, g):
         x = ctypes.c_uint64()
@@ -89,13 +113,13 @@ class PauliPlan:
         ncols = 1 if cols.ndim == 1 else cols.shape[1]
         cols = numpy.asfortranarray(cols) if cols.ndim == 2 else numpy.ascontiguousarray(cols)
         out = numpy.empty_like(cols, order='F' if cols.ndim == 2 else 'C')
-        _lib.call('ofb_apply_host', self.handle, _lib.ptr(cols), _lib.ptr(out), c_int(ncols))
+        _lib.call('ofb_apply_host', self._apply_handle, _lib.ptr(cols), _lib.ptr(out), c_int(ncols))
         return out
 
     def expectation_host(self, state):
         state = numpy.ascontiguousarray(state, dtype=numpy.complex128).reshape(-1)
         out = (ctypes.c_double * 2)()
-        _lib.call('ofb_expectation_host', self.handle, _lib.ptr(state), out)
+        _lib.call('ofb_expectation_host', self._apply_handle, _lib.ptr(state), out)
         return complex(out[0], out[1])
 
     def diagonal_host(self):
@@ -148,24 +172,25 @@ class PauliPlan:
 
     # ---- device-pointer calls (Krylov loops, bench) ----------------------------
     def apply_device(self, d_in, d_out, ncols=1, ld=None, stream=None):
-        _lib.call('ofb_apply', self.handle, c_void_p(d_in), c_void_p(d_out), c_int(ncols),
+        _lib.call('ofb_apply', self._apply_handle, c_void_p(d_in), c_void_p(d_out), c_int(ncols),
                   c_int64(self.dim if ld is None else ld), c_void_p(stream))
 
     def apply_groups_device(self, d_in, d_out, local_bits, index_base, g_begin, g_end, accumulate,
                             stream=None):
-        _lib.call('ofb_apply_groups', self.handle, c_void_p(d_in), c_void_p(d_out), c_int(local_bits),
+        _lib.call('ofb_apply_groups', self._apply_handle, c_void_p(d_in), c_void_p(d_out), c_int(local_bits),
                   ctypes.c_uint64(index_base), c_int64(g_begin), c_int64(g_end), c_int(accumulate),
                   c_void_p(stream))
 
     def expectation_device(self, d_state, stream=None):
         out = (ctypes.c_double * 2)()
-        _lib.call('ofb_expectation', self.handle, c_void_p(d_state), out, c_void_p(stream))
+        _lib.call('ofb_expectation', self._apply_handle, c_void_p(d_state), out, c_void_p(stream))
         return complex(out[0], out[1])
 
     def diagonal_device(self, d_out, stream=None):
         _lib.call('ofb_diagonal', self.handle, c_void_p(d_out), c_void_p(stream))
 
     def close(self):
+        self._drop_k1()
         if getattr(self, 'handle', None):
             _lib.call('ofb_plan_destroy', self.handle)
             self.handle = None

@@ -108,6 +108,96 @@ def group_conditions(x, z, c):
     return group_x, mask1, mask2, flags
 
 
+def reduce_terms(x, z, c, group_x, mask1, mask2, flags, class_shift=6, class_mask=15):
+    """Term table that equals the original one ON THE SUPPORT of every group, with one term per
+    symmetry orbit.
+
+    On the support of a group chi_m(j) = s for each of its conditions, so the strings z and z ^ m
+    have the same sign pattern up to the constant s: the orbit {z, z ^ m1, z ^ m2, z ^ m1 ^ m2}
+    collapses to its representative with the coefficient  sum_u s_u k_u  (= 2 k or 4 k for an
+    exactly symmetric group).  A kernel that zeroes the amplitudes outside the support -- the
+    support-hint variant does -- can therefore sum a quarter of the terms of a mixed-spin double
+    excitation on a quarter of the amplitudes.  The table is only valid together with the hints.
+
+    Returns (x', z', c') with Pauli coefficients c' (the library re-derives the phase from the
+    masks), groups in ascending x, representatives in their original relative order."""
+    x = numpy.asarray(x, dtype=numpy.uint64)
+    z = numpy.asarray(z, dtype=numpy.uint64)
+    k = _phased(x, z, c)
+    order = numpy.argsort(x, kind='stable')
+    xs = x[order].tolist()
+    zs = z[order].tolist()
+    ks = k[order].tolist()
+    group_of = {int(gx): g for g, gx in enumerate(numpy.asarray(group_x).tolist())}
+    out_x, out_z, out_k = [], [], []
+    start = 0
+    total = len(xs)
+    while start < total:
+        end = start
+        while end < total and xs[end] == xs[start]:
+            end += 1
+        g = group_of[xs[start]]
+        gens = []
+        if flags[g] & 1:
+            gens.append((int(mask1[g]), -1.0 if (flags[g] >> 1) & 1 else 1.0))
+        if flags[g] & 4:
+            gens.append((int(mask2[g]), -1.0 if (flags[g] >> 3) & 1 else 1.0))
+        if not gens:
+            out_x += xs[start:end]
+            out_z += zs[start:end]
+            out_k += ks[start:end]
+            start = end
+            continue
+        # the elements of the symmetry group generated by the conditions: (mask, sign)
+        elements = [(0, 1.0)]
+        for m, s in gens:
+            elements += [(e ^ m, se * s) for e, se in elements]
+        index = {zt: t for t, zt in enumerate(zs[start:end])}
+        orbits, seen = [], set()
+        for zt in zs[start:end]:
+            if zt in seen:
+                continue
+            members = []
+            for e, _ in elements:
+                if (zt ^ e) not in index:
+                    raise ValueError('term table is not invariant under its own support hints')
+                members.append(zt ^ e)
+                seen.add(zt ^ e)
+            orbits.append(members)
+        # Any member can represent its orbit.  The kernel pays 2 * 16 multiply-adds per distinct
+        # "class" (the z bits CLASS_SHIFT..CLASS_SHIFT+3) among a group's terms, so pick the
+        # representatives that share as few classes as possible (greedy cover).
+        def cls(zv):
+            return (zv >> class_shift) & class_mask
+        chosen = [None] * len(orbits)
+        while any(r is None for r in chosen):
+            counts = {}
+            for o, members in enumerate(orbits):
+                if chosen[o] is None:
+                    for w in {cls(zv) for zv in members}:
+                        counts[w] = counts.get(w, 0) + 1
+            best = min(counts, key=lambda w: (-counts[w], w))
+            for o, members in enumerate(orbits):
+                if chosen[o] is None:
+                    hit = [zv for zv in members if cls(zv) == best]
+                    if hit:
+                        chosen[o] = min(hit)
+        for rep in chosen:
+            coeff = 0.0
+            for e, se in elements:
+                coeff += se * ks[start + index[rep ^ e]]
+            out_x.append(xs[start])
+            out_z.append(rep)
+            out_k.append(coeff)
+        start = end
+    xr = numpy.array(out_x, dtype=numpy.uint64)
+    zr = numpy.array(out_z, dtype=numpy.uint64)
+    kr = numpy.array(out_k, dtype=numpy.complex128)
+    y = numpy.bitwise_count(xr & zr)
+    cr = kr * numpy.array([1, 1j, -1, -1j])[y % 4]  # undo the gather-form phase: c = k (+i)^y
+    return xr, zr, cr
+
+
 def needed_fraction(flags):
     """Share of (group, amplitude) gathers that remain: 1/2 per condition."""
     flags = numpy.asarray(flags)

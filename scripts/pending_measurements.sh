@@ -19,6 +19,7 @@ hints)
     OFB_TEST_EXPERIMENTAL=1 python -m pytest tests/test_gpu_support_hints.py -m gpu -x -q 2>&1 | tail -3
     for w in hub30 mol26; do
         python scripts/quick_apply_bench.py $w
+        OFB_SUPPORT_HINTS=hints python scripts/quick_apply_bench.py $w
         OFB_SUPPORT_HINTS=1 python scripts/quick_apply_bench.py $w
     done
     ;;

@@ -32,14 +32,15 @@ def _state(n, seed):
     return v / numpy.linalg.norm(v)
 
 
+@pytest.mark.parametrize('reduce', [False, True], ids=['hints', 'hints+reduced'])
 @pytest.mark.parametrize('name,builder,n', CASES, ids=[c[0] for c in CASES])
-def test_hints_do_not_change_the_result(name, builder, n):
+def test_hints_do_not_change_the_result(name, builder, n, reduce):
     from openfermion_b200.plan import PauliPlan
     op = builder()
     x, z, c = compiler.compile_qubit_operator(op, n)
     plain = PauliPlan(n, x, z, c)
     hinted = PauliPlan(n, x, z, c)
-    hinted.set_support_hints(x, z, c)
+    hinted.set_support_hints(x, z, c, reduce=reduce)
     v = _state(n, 3)
     want = plain.apply_host(v)
     got = hinted.apply_host(v)
@@ -47,6 +48,11 @@ def test_hints_do_not_change_the_result(name, builder, n):
     assert abs(hinted.expectation_host(v) - plain.expectation_host(v)) <= 1e-12 * numpy.sum(numpy.abs(c))
     if 'hubbard' in name or 'molecular' in name:
         assert hinted.support_fraction < 0.6
+        if reduce:
+            assert hinted.n_reduced_terms < plain.n_terms
+    # diagonal and CSC keep the full table
+    if n <= 14 and not numpy.any(c.imag):
+        assert numpy.array_equal(hinted.diagonal_host(), plain.diagonal_host())
 
 
 def test_hints_with_shards_and_accumulate():
