@@ -330,7 +330,8 @@ k_apply1(const double2 *__restrict__ vin, double2 *__restrict__ vout,
          const Segment *__restrict__ segs, const uint32_t *__restrict__ seg_term_begin,
          uint32_t s0, uint32_t s1,
          const TermZC *__restrict__ zc_re, const TermZC *__restrict__ zc_im, uint32_t dim,
-         uint64_t index_base, int accumulate, double2 *__restrict__ partials) {
+         uint64_t index_base, int accumulate, double2 *__restrict__ partials,
+         const SegCond *__restrict__ conds) {
     const uint32_t j = blockIdx.x * BLOCK + threadIdx.x;
     const bool valid = j < dim;
     const uint64_t jz = index_base | j;
@@ -344,6 +345,12 @@ k_apply1(const double2 *__restrict__ vin, double2 *__restrict__ vout,
         const Segment sd = segs[s];
         const uint32_t kind = sd.kind_runs >> 30;
         const uint32_t tb = seg_term_begin[s], te = tb + ((sd.kind_runs >> 8) & 0xffffu);
+        if (conds) {  // support hints: bit 0 of the tile kernel's need mask (this amplitude is "r = 0")
+            const SegCond cd = conds[s];
+            const uint32_t q1 = ((uint32_t)__popc((uint32_t)jz & cd.m1) + cd.v) & 1u;
+            const uint32_t q2 = ((uint32_t)__popc((uint32_t)jz & cd.m2) + (cd.v >> 1)) & 1u;
+            if (((cd.pat ^ (q1 - 1u)) & ((cd.pat >> 16) ^ (q2 - 1u)) & 1u) == 0u) continue;
+        }
         const double2 v = valid ? vin[j ^ ((uint32_t)sd.x & (dim - 1))] : make_double2(0.0, 0.0);
         double sr = 0.0, si = 0.0;
         for (uint32_t t = tb; t < te; ++t) {
@@ -444,7 +451,8 @@ static int launch_apply_impl(ofb_plan *p, const void *d_in, void *d_out, int loc
         k_apply1<EXPECT><<<(unsigned)blocks, BLOCK, 0, s>>>(in, out, p->d_segs, p->d_seg_term_begin,
                                                             s0, s1, p->d_zc, p->d_zc_im,
                                                             (uint32_t)dim, index_base, accumulate,
-                                                            partials);
+                                                            partials,
+                                                            (p->has_cond && p->z_fits32) ? p->d_conds : nullptr);
     }
     OFB_LAUNCH_CHECK();
     return OFB_OK;

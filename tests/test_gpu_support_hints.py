@@ -16,6 +16,8 @@ pytestmark = [pytest.mark.gpu,
                                  reason='experimental kernel variant, set OFB_TEST_EXPERIMENTAL=1')]
 
 CASES = [
+    ('hubbard_2x2_n8_small_state_kernel', lambda: hamiltonians.hubbard_jw(2, 2, 1.0, 4.0, 0.3, 0.2), 8),
+    ('molecular_n6_small_state_kernel', lambda: hamiltonians.molecular_jw(3, seed=2), 6),
     ('hubbard_2x4_n16', lambda: hamiltonians.hubbard_jw(2, 4), 16),
     ('hubbard_2x5_mu_h_n20', lambda: hamiltonians.hubbard_jw(2, 5, 1.0, 4.0, 0.3, 0.2), 20),
     ('hubbard_2x4_bk_n16', lambda: hamiltonians.hubbard_jw(2, 4, encoding='bk'), 16),
