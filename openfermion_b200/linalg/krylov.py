@@ -168,7 +168,7 @@ def as_device_operator(operator):
     if isinstance(operator, (PlanOperator, SectorOperator, CsrOperator, HostCallbackOperator)):
         return operator
     if isinstance(operator, SectorLinearQubitOperator):
-        return SectorOperator(operator.plan, operator.sector)
+        return SectorOperator(operator.apply_plan, operator.sector)
     if isinstance(operator, LinearQubitOperator):
         return PlanOperator(operator.plan)
     if isinstance(operator, ParallelLinearQubitOperator):

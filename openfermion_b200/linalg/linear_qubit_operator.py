@@ -149,6 +149,7 @@ class SectorLinearQubitOperator(scipy.sparse.linalg.LinearOperator):
         self.sz_value = sz_value
         self._spin_maps = (up_index, down_index)
         self._sector = None
+        self._apply_plan = None
         if sz_value is None:
             dim = sectors.number_sector_dim(self.n_qubits, n_electrons)
         elif up_index is None and down_index is None:
@@ -161,6 +162,25 @@ class SectorLinearQubitOperator(scipy.sparse.linalg.LinearOperator):
     @property
     def plan(self):
         return self.linear_qubit_operator.plan
+
+    @property
+    def apply_plan(self):
+        """The plan the sector matvec / expectation kernels run on.  Experimental
+        (OFB_SUPPORT_HINTS=1, openfermion_b200/support.py): the orbit-reduced term table, for the
+        group conditions that sector membership implies; otherwise the full plan."""
+        if self._apply_plan is None:
+            self._apply_plan = self.plan
+            tables = self.sector.tables
+            if os.environ.get('OFB_SUPPORT_HINTS') == '1' and tables is not None:
+                from openfermion_b200 import support
+                x, z, c = compile_qubit_operator(self.qubit_operator, self.n_qubits)
+                group_x, mask1, mask2, flags = support.group_conditions(x, z, c)
+                flags = support.conditions_implied_by_sector(group_x, mask1, mask2, flags,
+                                                             tables.plus, tables.minus)
+                if numpy.any(flags):
+                    xr, zr, cr = support.reduce_terms(x, z, c, group_x, mask1, mask2, flags)
+                    self._apply_plan = PauliPlan(self.n_qubits, xr, zr, cr)
+        return self._apply_plan
 
     @property
     def sector(self):
@@ -183,11 +203,11 @@ class SectorLinearQubitOperator(scipy.sparse.linalg.LinearOperator):
     def _matvec(self, x):
         arr = numpy.asarray(x)
         vec = numpy.ascontiguousarray(arr.reshape(-1), dtype=numpy.complex128)
-        return self.sector.apply_host(self.plan, vec).reshape(arr.shape)
+        return self.sector.apply_host(self.apply_plan, vec).reshape(arr.shape)
 
     def _matmat(self, X):
         X = numpy.asarray(X)
-        return self.sector.apply_host(self.plan, numpy.asfortranarray(X, dtype=numpy.complex128))
+        return self.sector.apply_host(self.apply_plan, numpy.asfortranarray(X, dtype=numpy.complex128))
 
 
 def apply_operator(args):

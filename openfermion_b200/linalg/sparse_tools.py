@@ -186,7 +186,7 @@ def expectation(operator, state):
         if isinstance(operator, SectorLinearQubitOperator):
             if state.size != operator.shape[1]:
                 raise ValueError('Dimension mismatch')
-            return operator.sector.expectation_host(operator.plan, state)
+            return operator.sector.expectation_host(operator.apply_plan, state)
         applied = krylov.apply_any(operator, state)
         if len(state.shape) == 1:
             return numpy.dot(numpy.conjugate(state), applied)

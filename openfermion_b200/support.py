@@ -198,6 +198,48 @@ def reduce_terms(x, z, c, group_x, mask1, mask2, flags, class_shift=6, class_mas
     return xr, zr, cr
 
 
+def conditions_implied_by_sector(group_x, mask1, mask2, flags, plus, minus):
+    """Keep only the conditions that hold automatically inside a symmetry sector.
+
+    The sector kernels (csrc/sector.cu) evaluate a group at j only if j and j ^ x are both
+    members, i.e. satisfy |j & plus_k| - |j & minus_k| = value_k for every constraint k.  Both
+    memberships together force  parity(j & x & (plus_k | minus_k)) = (|x & plus_k| - |x & minus_k|)/2
+    mod 2, and with it every GF(2) combination over k.  A group condition inside that span never
+    fails where the sector kernel evaluates the group, so the orbit-reduced table
+    (`reduce_terms`) can be used there without any change to the kernel.  Returns new flags."""
+    flags = numpy.array(flags, dtype=numpy.uint8)
+    out = numpy.zeros_like(flags)
+    plus = [int(p) for p in plus]
+    minus = [int(m) for m in minus]
+    for g, xg in enumerate(numpy.asarray(group_x).tolist()):
+        if not flags[g]:
+            continue
+        implied = {}
+        base = []
+        for p, m in zip(plus, minus):
+            a, b = bin(xg & p).count('1'), bin(xg & m).count('1')
+            if (a - b) % 2:
+                base = None  # no member j has a member partner j ^ x: the group never acts
+                break
+            base.append((xg & (p | m), ((a - b) // 2) % 2))
+        if base is None:
+            out[g] = flags[g]  # anything is "implied" on an empty set
+            continue
+        for subset in range(1, 1 << len(base)):
+            m_acc, v_acc = 0, 0
+            for k, (mk, vk) in enumerate(base):
+                if (subset >> k) & 1:
+                    m_acc ^= mk
+                    v_acc ^= vk
+            if m_acc:
+                implied[m_acc] = v_acc
+        if flags[g] & 1 and implied.get(int(mask1[g])) == ((flags[g] >> 1) & 1):
+            out[g] |= flags[g] & 0b0011
+        if flags[g] & 4 and implied.get(int(mask2[g])) == ((flags[g] >> 3) & 1):
+            out[g] |= flags[g] & 0b1100
+    return out
+
+
 def needed_fraction(flags):
     """Share of (group, amplitude) gathers that remain: 1/2 per condition."""
     flags = numpy.asarray(flags)

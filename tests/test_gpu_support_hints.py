@@ -90,3 +90,25 @@ def test_hints_with_shards_and_accumulate():
                     first = False
             outs.append(krylov.download(1 << n, d_out.ptr))
         assert helpers.close(outs[1], outs[0], 1e-13)
+
+
+@pytest.mark.parametrize('kind', ['sz_number', 'number'])
+def test_sector_kernel_on_the_reduced_table(kind, monkeypatch):
+    """SectorLinearQubitOperator.apply_plan under OFB_SUPPORT_HINTS=1: the unchanged sector kernel
+    on the orbit-reduced table (only the conditions sector membership implies)."""
+    from openfermion_b200.linalg import SectorLinearQubitOperator, expectation
+    for op, n in ((hamiltonians.hubbard_jw(2, 4, 1.0, 4.0, 0.3, 0.2), 16), (hamiltonians.molecular_jw(7, seed=4), 14)):
+        kwargs = dict(n_electrons=6, sz_value=0.0) if kind == 'sz_number' else dict(n_electrons=5)
+        monkeypatch.delenv('OFB_SUPPORT_HINTS', raising=False)
+        plain = SectorLinearQubitOperator(op, n, **kwargs)
+        rng = numpy.random.default_rng(1)
+        v = rng.normal(size=plain.shape[0]) + 1j * rng.normal(size=plain.shape[0])
+        want = plain * v
+        e_want = expectation(plain, v)
+        monkeypatch.setenv('OFB_SUPPORT_HINTS', '1')
+        reduced = SectorLinearQubitOperator(op, n, **kwargs)
+        got = reduced * v
+        assert helpers.close(got, want, 1e-13)
+        assert abs(expectation(reduced, v) - e_want) <= 1e-12 * abs(e_want)
+        if kind == 'sz_number':
+            assert reduced.apply_plan.n_terms < plain.plan.n_terms

@@ -160,3 +160,59 @@ def test_kernel_need_mask_equals_the_definition():
                 if flag & 4:
                     want &= (bin(j & mask2_g).count('1') & 1) == ((flag >> 3) & 1)
                 assert bool((need >> r) & 1) == want
+
+
+# ---- inside symmetry sectors ---------------------------------------------------------------
+def _sector_emulation(n, x, z, c, tables, v):
+    """What k_sector_apply computes: out[p] = sum_g [j ^ x_g member] S_g(j) in[pos(j ^ x_g)]."""
+    k = support._phased(x, z, c)
+    basis = tables.basis()
+    out = numpy.zeros(tables.dim, dtype=numpy.complex128)
+    for xg in numpy.unique(x):
+        partner = basis ^ xg
+        ok = tables.member(partner)
+        s = numpy.zeros(tables.dim, dtype=numpy.complex128)
+        for t in numpy.nonzero(x == xg)[0]:
+            s += k[t] * (1.0 - 2.0 * po.bit_parity(basis & z[t]))
+        pos = numpy.where(ok, tables.position(numpy.where(ok, partner, basis)), 0)
+        out += numpy.where(ok, s * v[pos], 0.0)
+    return out
+
+
+@pytest.mark.parametrize('kind', ['sz_number', 'number', 'sz'])
+@pytest.mark.parametrize('name,builder,n', [
+    ('hubbard_2x3', lambda: hamiltonians.hubbard_jw(2, 3, 1.0, 4.0, 0.3, 0.2), 12),
+    ('molecular_5', lambda: hamiltonians.molecular_jw(5, seed=4), 10),
+])
+def test_reduced_table_inside_a_sector(name, builder, n, kind):
+    """Conditions implied by sector membership (support.conditions_implied_by_sector) let the
+    unchanged sector kernel run on the orbit-reduced table.  With S_z and N fixed every
+    condition of a spin-conserving Hamiltonian is implied; with N alone only the total-parity
+    ones are, and the rest must stay unreduced."""
+    from openfermion_b200 import sectors
+    op = builder()
+    x, z, c = compile_qubit_operator(op, n)
+    if kind == 'sz_number':
+        tables = sectors.sz_number_sector_tables(n, 0.0, 4)
+    elif kind == 'number':
+        tables = sectors.number_sector_tables(n, 4)
+    else:
+        tables = sectors.sz_sector_tables(n, 1.0)
+    group_x, mask1, mask2, flags = support.group_conditions(x, z, c)
+    implied = support.conditions_implied_by_sector(group_x, mask1, mask2, flags, tables.plus, tables.minus)
+    assert numpy.all((implied & ~flags) == 0)
+    xr, zr, cr = support.reduce_terms(x, z, c, group_x, mask1, mask2, implied)
+    rng = numpy.random.default_rng(8)
+    v = rng.normal(size=tables.dim) + 1j * rng.normal(size=tables.dim)
+    want = _sector_emulation(n, x, z, c, tables, v)
+    got = _sector_emulation(n, xr, zr, cr, tables, v)
+    assert numpy.max(numpy.abs(got - want)) <= 1e-13 * numpy.max(numpy.abs(want))
+    if kind == 'sz_number':
+        assert numpy.array_equal(implied, flags) and len(cr) < 0.7 * len(c)
+    if kind == 'number':  # mixed-spin double excitations keep their spin conditions unreduced
+        assert len(c) >= len(cr)
+        # using conditions that are NOT implied would be wrong: the check has teeth
+        xb, zb, cb = support.reduce_terms(x, z, c, group_x, mask1, mask2, flags)
+        bad = _sector_emulation(n, xb, zb, cb, tables, v)
+        if len(cb) < len(cr):
+            assert numpy.max(numpy.abs(bad - want)) > 1e-6 * numpy.max(numpy.abs(want))
