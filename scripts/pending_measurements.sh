@@ -22,6 +22,8 @@ hints)
         OFB_SUPPORT_HINTS=hints python scripts/quick_apply_bench.py $w
         OFB_SUPPORT_HINTS=1 python scripts/quick_apply_bench.py $w
     done
+    python scripts/sector_bench.py hub44_half mol28
+    OFB_SUPPORT_HINTS=1 python scripts/sector_bench.py hub44_half mol28
     ;;
 multi)
     N="${2:-2}"
