@@ -119,8 +119,13 @@ def compare_bases(n, rank, world, local, steps=5, warmup=3):
                               'term_amp_per_s': sop.n_terms * float(1 << n) / (float(t.item()) / 1e3),
                               'vHv': [e.real, e.imag]}))
         sop.close()
-        del vin, vout, sop
         torch.cuda.synchronize()
+        # free the 2^n-sized buffers now: the operator holds reference cycles (bound methods)
+        for buf in [vin, vout] + list(sop._staging):
+            buf.free()
+        del vin, vout, sop
+        import gc
+        gc.collect()
         dist.barrier()
 
 
