@@ -247,12 +247,19 @@ class ShardedPauliOperator:
             self._peer_vectors[vec.ptr] = ptrs
 
     def close(self):
+        """Unmap the peers' buffers and free this rank's staging shards (call after the last
+        matvec has completed on the device)."""
         for p in self._opened:
             try:
                 self._lib.call('ofb_ipc_close_handle', ctypes.c_void_p(p))
             except Exception:
                 pass
         self._opened = []
+        self._peer_vectors = {}
+        for buf in self._staging:
+            if hasattr(buf, 'free'):
+                buf.free()
+        self._staging = []
 
     # -- the sharded matvec --------------------------------------------------------------------
     def _matvec_ce(self, vin, vout):
