@@ -216,3 +216,67 @@ def test_reduced_table_inside_a_sector(name, builder, n, kind):
         bad = _sector_emulation(n, xb, zb, cb, tables, v)
         if len(cb) < len(cr):
             assert numpy.max(numpy.abs(bad - want)) > 1e-6 * numpy.max(numpy.abs(want))
+
+
+def test_synthetic_symmetric_groups_with_complex_coefficients():
+    """Groups built to be invariant under chosen (m, s) pairs -- complex coefficients, both signs,
+    Y factors in the strings -- next to groups without any symmetry."""
+    rng = numpy.random.default_rng(12)
+    n = 9
+    xs, zs, cs = [], [], []
+    planted = {}
+    for trial in range(12):
+        xg = int(rng.integers(1, 1 << n))
+        if xg in planted:
+            continue
+        gens = []
+        for _ in range(int(rng.integers(0, 3))):
+            m = int(rng.integers(1, 1 << n))
+            if all(m != g[0] for g in gens) and (len(gens) < 1 or m != gens[0][0]):
+                gens.append((m, float(rng.choice([-1.0, 1.0]))))
+        elements = [(0, 1.0)]
+        for m, s in gens:
+            elements += [(e ^ m, se * s) for e, se in elements]
+        if len({e for e, _ in elements}) != len(elements):
+            continue  # dependent generators
+        members = {}
+        consistent = True
+        for _ in range(int(rng.integers(1, 4))):
+            z0 = int(rng.integers(0, 1 << n))
+            k0 = complex(rng.normal(), rng.normal())
+            for e, se in elements:
+                if (z0 ^ e) in members:
+                    consistent = False
+                members[z0 ^ e] = se * k0
+        if not consistent:
+            continue
+        planted[xg] = gens
+        for zt, kt in members.items():
+            y = bin(xg & zt).count('1')
+            xs.append(xg)
+            zs.append(zt)
+            cs.append(kt * [1, 1j, -1, -1j][y % 4])  # Pauli coefficient whose phased value is kt
+    x = numpy.array(xs, dtype=numpy.uint64)
+    z = numpy.array(zs, dtype=numpy.uint64)
+    c = numpy.array(cs, dtype=numpy.complex128)
+    group_x, mask1, mask2, flags = support.group_conditions(x, z, c)
+    for g, xg in enumerate(group_x.tolist()):
+        want = min(len(planted[xg]), 2)
+        assert (flags[g] & 1) + ((flags[g] >> 2) & 1) >= want
+    xr, zr, cr = support.reduce_terms(x, z, c, group_x, mask1, mask2, flags)
+    j = numpy.arange(1 << n, dtype=numpy.uint64)
+    v = rng.normal(size=1 << n) + 1j * rng.normal(size=1 << n)
+    k, kr = support._phased(x, z, c), support._phased(xr, zr, cr)
+    full = numpy.zeros(1 << n, dtype=numpy.complex128)
+    hinted = numpy.zeros(1 << n, dtype=numpy.complex128)
+    for g, xg in enumerate(group_x):
+        need = numpy.ones(1 << n, dtype=bool)
+        if flags[g] & 1:
+            need &= po.bit_parity(j & mask1[g]) == ((flags[g] >> 1) & 1)
+        if flags[g] & 4:
+            need &= po.bit_parity(j & mask2[g]) == ((flags[g] >> 3) & 1)
+        gathered = v[(j ^ xg).astype(numpy.int64)]
+        full += _coefficient_function(x, z, k, xg, n) * gathered
+        hinted += numpy.where(need, _coefficient_function(xr, zr, kr, xg, n), 0.0) * gathered
+    assert numpy.max(numpy.abs(hinted - full)) <= 1e-13 * numpy.max(numpy.abs(full))
+    assert len(cr) < len(c)
