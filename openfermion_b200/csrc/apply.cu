@@ -268,7 +268,12 @@ k_apply_tile(const double2 *__restrict__ vin, double2 *__restrict__ vout,
                 const uint32_t q2 = ((uint32_t)__popc(j_lo & cd.m2) + (cd.v >> 1)) & 1u;
                 const uint32_t need = (cd.pat ^ (q1 - 1u)) & ((cd.pat >> 16) ^ (q2 - 1u)) & ((1u << RT) - 1u);
                 if (need == 0u) continue;
-                load_tile_needed(vin, jx, need, v);
+                // conditions that do not involve the class bits leave a thread all or nothing:
+                // the common case takes the plain loads (immediate offsets, no predicates)
+                if (need == ((1u << RT) - 1u))
+                    load_tile(vin, jx, v);
+                else
+                    load_tile_needed(vin, jx, need, v);
             } else {
                 load_tile(vin, jx, v);
             }
