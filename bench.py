@@ -339,6 +339,7 @@ def run_single(args):
         'warmup': args.warmup, 'ms_per_step': ms.value / args.steps, 'higher_is_better': True,
         'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f64', 'data': 'synthetic',
         'config': {'workload': name, 'n_qubits': n, 'terms': T, 'x_groups': G,
+                   'support_hints': os.environ.get('OFB_SUPPORT_HINTS'),  # experimental, None = off
                    'l2_policy': 'inputs exceed L2 (state vector %.1f GB per buffer)' % (dim * 16 / 1e9),
                    'timing': 'CUDA events on the launch stream', 'self_check_rel_err': check},
         'clocks': clocks,

@@ -601,6 +601,7 @@ def bench_main(args, metric, unit, clock_sampler_cls, measured_peak):
                        'exchange': mode, 'remote_patterns': len(layout.remote_patterns),
                        'remote_patterns_top_qubit_sharding': len(natural_layout.remote_patterns),
                        'exchange_bytes_per_rank_per_step': layout.exchange_bytes_per_matvec() if mode in ('nccl', 'ce') else None,
+                       'support_hints': os.environ.get('OFB_SUPPORT_HINTS'),  # experimental, None = off
                        'l2_policy': 'inputs exceed L2 (%.1f GB per shard)' % (dim_local * 16 / 1e9),
                        'timing': 'CUDA events, max over ranks', 'expectation_check': [e.real, e.imag],
                        'one_gpu_same_workload': one_gpu_base(n),
