@@ -94,7 +94,7 @@ def test_qubit_davidson_matches_reference_run_at_12_qubits():
     op = copy.deepcopy(helpers.qubit_case_operator(case))
     op.compress()
     numpy.random.seed(7)
-    success, values, vectors = QubitDavidson(op, 12).get_lowest_n(2, max_iterations=60)
+    success, values, vectors = QubitDavidson(op, 12).get_lowest_n(2, max_iterations=150)
     assert success
     assert numpy.max(numpy.abs(numpy.sort(values) - numpy.sort(case['davidson_lowest2']))) < 1e-5
     assert abs(min(values) - float(case['e0'])) < 1e-5
