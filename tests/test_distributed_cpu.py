@@ -154,3 +154,61 @@ def test_shard_layout_patterns():
     one = ShardLayout(5, 1, numpy.array([0, 3, 17], dtype=numpy.uint64))
     assert one.remote_patterns == [] and one.local_pattern == (0, 0, 3)
     assert ShardLayout(6, 4, numpy.array([1], dtype=numpy.uint64)).peer(2, 3) == 1
+
+
+def _observable_worker(rank, world, port, out_dir):
+    """An observable applied on shards cut by ANOTHER operator's symmetry basis."""
+    os.environ['MASTER_ADDR'] = '127.0.0.1'
+    os.environ['MASTER_PORT'] = str(port)
+    dist.init_process_group('gloo', rank=rank, world_size=world)
+    try:
+        from openfermion_b200.compiler import compile_qubit_operator
+        from openfermion_b200.shard_basis import ShardBasis
+        n = 8
+        hamiltonian = hamiltonians.hubbard_jw(2, 2)
+        basis = ShardBasis.for_sharding(n, world.bit_length() - 1, compile_qubit_operator(hamiltonian, n)[0],
+                                        local_order='locality')
+        observable = hamiltonians.random_pauli_sum(n, 25, 9, True)  # shares no symmetry with H
+        ctx = {}
+
+        def local_apply(vin, vout, g0, g1, accumulate):
+            x, z, c = ctx['tables']
+            layout, j, jg, group_of = ctx['layout'], ctx['j'], ctx['jg'], ctx['group_of']
+            out = vout.array
+            if not accumulate:
+                out[:] = 0
+            for t in range(len(c)):
+                if g0 <= group_of[t] < g1:
+                    phase = c[t] * (-1j) ** bin(int(x[t] & z[t])).count('1')
+                    sign = 1.0 - 2.0 * po.bit_parity(jg & z[t]).astype(float)
+                    out += phase * sign * vin.array[(j ^ (x[t] & numpy.uint64(layout.local_dim - 1))).astype(numpy.int64)]
+
+        op = ShardedPauliOperator(
+            observable, n, dist=dist, mode='nccl', local_apply=local_apply,
+            vector_factory=lambda: _HostVec(1 << (n - (world.bit_length() - 1))),
+            tensor_of=lambda v: torch.from_numpy(v.array.view(numpy.float64)), basis=basis)
+        layout = op.layout
+        j = numpy.arange(layout.local_dim, dtype=numpy.uint64)
+        ctx.update(tables=op._tables, layout=layout, j=j, jg=j | numpy.uint64(rank << layout.local_bits),
+                   group_of=numpy.searchsorted(layout.group_x, op._tables[0]))
+        rng = numpy.random.default_rng(6)
+        full = rng.normal(size=1 << n) + 1j * rng.normal(size=1 << n)
+        vin, vout = op.new_vector(), op.new_vector()
+        vin.array[:] = op.shard_of(full)
+        op.matvec(vin, vout)
+        want_full = po.matvec(observable.terms, n, full)
+        err = float(numpy.max(numpy.abs(vout.array - op.shard_of(want_full))))
+        total = TorchComm(dist, 'cpu').allsum(numpy.vdot(vin.array, vout.array))
+        numpy.save(os.path.join(out_dir, 'o%d.npy' % rank),
+                   numpy.array([err, abs(total - numpy.vdot(full, want_full))]))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_observable_in_the_basis_of_another_operator(tmp_path):
+    world = 4
+    mp.start_processes(_observable_worker, args=(world, _free_port(), str(tmp_path)), nprocs=world,
+                       join=True, start_method='fork')
+    for rank in range(world):
+        err, dot_err = numpy.load(tmp_path / ('o%d.npy' % rank))
+        assert err < 1e-12 and dot_err < 1e-11
