@@ -4,6 +4,7 @@
 #
 #   gpurun --timeout 300 -- 'bash scripts/pending_measurements.sh one'
 #   gpurun --timeout 300 -- 'bash scripts/pending_measurements.sh hints'
+#   gpurun --timeout 600 -- 'bash scripts/pending_measurements.sh ncu'
 #   gpurun --gpus 2 --timeout 200 -- 'bash scripts/pending_measurements.sh multi 2'
 #   gpurun --gpus 8 --timeout 300 -- 'bash scripts/pending_measurements.sh multi 8'
 set -u
@@ -24,6 +25,15 @@ hints)
     done
     python scripts/sector_bench.py hub44_half mol28
     OFB_SUPPORT_HINTS=1 python scripts/sector_bench.py hub44_half mol28
+    ;;
+ncu)
+    # one full capture of the hinted kernel per workload (only after the plain runs above exited 0)
+    for w in hub30 mol26; do
+        OFB_SUPPORT_HINTS=1 ncu --set full --clock-control none --import-source on -k regex:k_apply_tile \
+            -s 2 -c 1 -o "gpurun_out/k_apply_hints_${w}" python scripts/quick_apply_bench.py $w \
+            > "gpurun_out/ncu_hints_${w}.log" 2>&1
+        ncu -i "gpurun_out/k_apply_hints_${w}.ncu-rep" --page raw --csv > "gpurun_out/k_apply_hints_${w}_raw.csv" 2>/dev/null
+    done
     ;;
 multi)
     N="${2:-2}"
