@@ -169,3 +169,34 @@ def test_natural_basis_is_a_no_op():
     assert numpy.array_equal(xp, x) and numpy.array_equal(zp, z) and numpy.array_equal(cp, c)
     assert numpy.array_equal(basis.shard_natural_indices(2, 4), numpy.arange(32, 48, dtype=numpy.uint64))
     assert ShardBasis.for_sharding(6, 0, x).identity
+
+
+@pytest.mark.parametrize('seed', range(6))
+def test_general_invertible_relabelling(seed):
+    """Any invertible binary matrix is a valid basis (the `basis=ShardBasis(...)` option): dense
+    random matrices, strings with every Y-count residue, complex coefficients."""
+    rng = numpy.random.default_rng(100 + seed)
+    n = 7
+    rows = [1 << b for b in range(n)]
+    for _ in range(60):
+        a, b = (int(v) for v in rng.integers(0, n, size=2))
+        if a != b:
+            rows[a] ^= rows[b]
+        if rng.random() < 0.3:
+            a, b = (int(v) for v in rng.integers(0, n, size=2))
+            rows[a], rows[b] = rows[b], rows[a]
+    basis = ShardBasis(n, rows)
+    op = hamiltonians.random_pauli_sum(n, 50, seed, True)
+    x, z, c = compile_qubit_operator(op, n)
+    xp, zp, cp = basis.transform_terms(x, z, c)
+    # a relabelling maps distinct strings to distinct strings and keeps |coefficients|
+    assert len({(int(a), int(b)) for a, b in zip(xp, zp)}) == len({(int(a), int(b)) for a, b in zip(x, z)})
+    assert numpy.array_equal(numpy.abs(cp), numpy.abs(c))
+    v = rng.normal(size=1 << n) + 1j * rng.normal(size=1 << n)
+    want = po.matvec(op.terms, n, v)
+    got = basis.to_natural(_gather_apply(n, xp, zp, cp, basis.from_natural(v)))
+    assert numpy.max(numpy.abs(got - want)) <= 1e-13 * numpy.max(numpy.abs(want))
+    # composing with the inverse relabelling gives the original table back
+    inverse = ShardBasis(n, basis.inv_rows)
+    xb, zb, cb = inverse.transform_terms(xp, zp, cp)
+    assert numpy.array_equal(xb, x) and numpy.array_equal(zb, z) and numpy.array_equal(cb, c)
