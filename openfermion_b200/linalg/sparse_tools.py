@@ -199,6 +199,33 @@ def variance(operator, state):
     return expectation(operator**2, state) - expectation(operator, state) ** 2
 
 
+def expectation_computational_basis_state(operator, computational_basis_state):
+    """<state|operator|state> for a normal-ordered FermionOperator and one computational basis
+    state (sparse_tools.py:693-737).  Host arithmetic on the symbolic terms, as in the
+    reference: only number-like terms p^ p and q^ p^ q p of occupied orbitals contribute.  The
+    state is a list of occupations or a sparse / dense vector with a single non-zero entry,
+    whose index is read least-significant bit = orbital 0 (the reference's convention here)."""
+    if ops.is_qubit_operator(operator):
+        raise NotImplementedError('Not yet implemented for QubitOperators.')
+    if not ops.is_fermion_operator(operator):
+        raise TypeError('operator must be a FermionOperator.')
+    checker = getattr(operator, 'is_normal_ordered', None)
+    if not (checker() if callable(checker) else ops.is_normal_ordered(operator)):
+        raise ValueError('operator must be a normal ordered.')
+    occupied = computational_basis_state
+    if not isinstance(occupied, list):
+        index = int(occupied.nonzero()[0][0])
+        occupied = [(index >> orbital) & 1 == 1 for orbital in range(index.bit_length())]
+    terms = operator.terms
+    value = terms.get((), 0.0)
+    filled = [orbital for orbital, flag in enumerate(occupied) if flag]
+    for position, p in enumerate(filled):
+        value += terms.get(((p, 1), (p, 0)), 0.0)
+        for q in filled[position + 1:]:
+            value -= terms.get(((q, 1), (p, 1), (q, 0), (p, 0)), 0.0)
+    return value
+
+
 def get_ground_state(sparse_operator, initial_guess=None):
     """Lowest eigenpair (sparse_tools.py:566-587: eigsh(k=1, which='SA')), computed by the
     device-resident Lanczos loop.  Returns (float eigenvalue, complex128[dim] eigenstate)."""

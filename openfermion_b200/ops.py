@@ -247,6 +247,18 @@ def normal_ordered(operator):
     return ordered
 
 
+def is_normal_ordered(operator):
+    """FermionOperator.is_normal_ordered (ops/operators/fermion_operator.py): in every term the
+    raising operators stand left of the lowering ones and indices descend within each kind."""
+    for term in operator.terms:
+        for left, right in zip(term, term[1:]):
+            if right[1] and not left[1]:
+                return False
+            if right[1] == left[1] and right[0] >= left[0]:
+                return False
+    return True
+
+
 def _class_names(obj):
     return {c.__name__ for c in type(obj).__mro__}
 

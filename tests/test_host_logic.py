@@ -283,3 +283,29 @@ def test_jw_sector_indices_match_reference_order():
     for sz in (-1.5, -1.0, 0.0, 0.5, 1.0):
         assert jw_sz_indices(sz, 8) == ref_sz(sz, 8)
     assert jw_sz_indices(-1.0, 8, n_electrons=4) == ref_sz(-1.0, 8, n_electrons=4)
+
+
+# ---- expectation_computational_basis_state (sparse_tools_test.py:674-740) --------------------
+def test_expectation_computational_basis_state_known_answers():
+    import scipy.sparse
+    from openfermion_b200.linalg import expectation_computational_basis_state as ecbs
+    from openfermion_b200.ops import FermionOperator, QubitOperator
+
+    def column(index):
+        return scipy.sparse.csc_matrix(([1], ([index], [0])), shape=(16, 1))
+    single = FermionOperator('3^ 3', 1.9) + FermionOperator('2^ 1')
+    two = FermionOperator('2^ 2', 1.9) + FermionOperator('2^ 1') + FermionOperator('2^ 1^ 2 1', -1.7)
+    identity = FermionOperator((), 1.1)
+    assert abs(ecbs(single, column(15)) - 1.9) < 1e-12
+    assert abs(ecbs(two, column(6)) - 3.6) < 1e-12
+    assert abs(ecbs(identity, column(6)) - 1.1) < 1e-12
+    assert abs(ecbs(single, [1, 1, 1, 1]) - 1.9) < 1e-12
+    assert abs(ecbs(two, [0, 1, 1]) - 3.6) < 1e-12
+    assert abs(ecbs(identity, [0, 1, 1]) - 1.1) < 1e-12
+    with pytest.raises(TypeError):
+        ecbs('never', column(6))
+    with pytest.raises(NotImplementedError):
+        ecbs(QubitOperator(), column(6))
+    bad_order = FermionOperator('2^ 2', 1.9) + FermionOperator('2^ 1') + FermionOperator('2^ 1 2 1^', -1.7)
+    with pytest.raises(ValueError):
+        ecbs(bad_order, [0, 1, 1])
