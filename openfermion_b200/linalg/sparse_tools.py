@@ -72,6 +72,44 @@ def kronecker_operators(*args):
     return functools.reduce(wrapped_kronecker, *args)
 
 
+def _embed_two_level_block(entries, first_qubit, n_block_qubits, n_qubits):
+    """CSC of  1 (x) B (x) 1  for a small block B given by its stored entries (row, col, value),
+    acting on qubits first_qubit .. first_qubit + n_block_qubits - 1: every stored entry of B
+    -- explicit zeros included, as scipy's Kronecker product keeps them -- appears once per
+    value of the other qubits.  Index arithmetic only; no Kronecker chain."""
+    right_bits = n_qubits - first_qubit - n_block_qubits
+    left = numpy.arange(1 << first_qubit, dtype=numpy.int64)[:, None, None]
+    right = numpy.arange(1 << right_bits, dtype=numpy.int64)[None, None, :]
+    block_rows = numpy.array([e[0] for e in entries], dtype=numpy.int64)[None, :, None]
+    block_cols = numpy.array([e[1] for e in entries], dtype=numpy.int64)[None, :, None]
+    values = numpy.array([e[2] for e in entries], dtype=numpy.complex128)[None, :, None]
+    rows = (((left << n_block_qubits) | block_rows) << right_bits) | right
+    cols = (((left << n_block_qubits) | block_cols) << right_bits) | right
+    data = numpy.broadcast_to(values, rows.shape)
+    dim = 1 << n_qubits
+    return scipy.sparse.csc_matrix((data.ravel(), (rows.ravel(), cols.ravel())), shape=(dim, dim),
+                                   dtype=numpy.complex128)
+
+
+def jw_sparse_givens_rotation(i, j, theta, phi, n_qubits):
+    """Matrix on the full 2^n space of a Givens rotation of the adjacent modes i, j = i + 1 in
+    the Jordan-Wigner encoding (sparse_tools.py:516-545).  A gate-building helper of the
+    reference (host, scipy there as here); same stored entries, explicit zeros included."""
+    if j != i + 1:
+        raise ValueError('Only adjacent modes can be rotated.')
+    if j > n_qubits - 1:
+        raise ValueError('Too few qubits requested.')
+    cosine, sine, phase = numpy.cos(theta), numpy.sin(theta), numpy.exp(1.0j * phi)
+    block = [(0, 0, 1.0), (1, 1, phase * cosine), (1, 2, -phase * sine), (2, 1, sine), (2, 2, cosine),
+             (3, 3, phase)]
+    return _embed_two_level_block(block, i, 2, n_qubits)
+
+
+def jw_sparse_particle_hole_transformation_last_mode(n_qubits):
+    """Particle-hole transformation of the last mode: 1 (x) X (sparse_tools.py:548-554)."""
+    return _embed_two_level_block([(0, 1, 1.0), (1, 0, 1.0)], n_qubits - 1, 1, n_qubits)
+
+
 def _tensor_fermion_terms(operator):
     """Terms of a PolynomialTensor-like object in the reference's iteration order
     (ops/representations/polynomial_tensor.py __iter__, conversions.py:117-121): constant

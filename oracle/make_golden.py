@@ -372,6 +372,21 @@ def ladder_cases():
         cases['kron_' + tag + '/shape'] = numpy.array(mat.shape)
     for tag, mat in (('a', a), ('b', b), ('c', c)):
         cases['kron_in_' + tag] = mat.toarray()
+    # gate-building helpers (sparse_tools.py:516-554); theta = 0 stores explicit zeros
+    from openfermion.linalg import (jw_sparse_givens_rotation,
+                                    jw_sparse_particle_hole_transformation_last_mode)
+    givens = [(0, 1, 0.3, 0.2, 3), (1, 2, 0.0, 0.0, 4), (0, 1, numpy.pi / 2, 0.1, 2), (4, 5, 1.1, -0.4, 6)]
+    cases['givens_args'] = numpy.array(givens, dtype=float)
+    for k, (i, j, theta, phi, n) in enumerate(givens):
+        mat = jw_sparse_givens_rotation(i, j, theta, phi, n)
+        cases['givens%d/indptr' % k] = mat.indptr
+        cases['givens%d/indices' % k] = mat.indices
+        cases['givens%d/data' % k] = mat.data
+    for n in (1, 3, 5):
+        mat = jw_sparse_particle_hole_transformation_last_mode(n)
+        cases['particle_hole%d/indptr' % n] = mat.indptr
+        cases['particle_hole%d/indices' % n] = mat.indices
+        cases['particle_hole%d/data' % n] = mat.data
     cases['names'] = numpy.array(names, dtype=str)
     numpy.savez_compressed(os.path.join(GOLDEN, 'ladder_cases.npz'), **cases)
     print('ladder_cases:', len(names), 'cases')

@@ -309,3 +309,27 @@ def test_expectation_computational_basis_state_known_answers():
     bad_order = FermionOperator('2^ 2', 1.9) + FermionOperator('2^ 1') + FermionOperator('2^ 1 2 1^', -1.7)
     with pytest.raises(ValueError):
         ecbs(bad_order, [0, 1, 1])
+
+
+def test_gate_matrix_helpers_match_reference():
+    # jw_sparse_givens_rotation / jw_sparse_particle_hole_transformation_last_mode
+    # (sparse_tools.py:516-554; sparse_tools_test.py:565-575 for the errors): golden matrices
+    # written by the reference, explicit zeros (theta = 0) included
+    import helpers
+    from openfermion_b200.linalg import (jw_sparse_givens_rotation,
+                                         jw_sparse_particle_hole_transformation_last_mode)
+    data = helpers.golden('ladder_cases.npz')
+    for k, (i, j, theta, phi, n) in enumerate(data['givens_args']):
+        mat = jw_sparse_givens_rotation(int(i), int(j), theta, phi, int(n))
+        assert mat.format == 'csc' and mat.nnz == 6 * 2 ** (int(n) - 2)
+        helpers.assert_csc_matches(mat, data['givens%d/indptr' % k], data['givens%d/indices' % k],
+                                   data['givens%d/data' % k], rtol=0)
+        assert numpy.array_equal(mat.data, data['givens%d/data' % k])
+    for n in (1, 3, 5):
+        mat = jw_sparse_particle_hole_transformation_last_mode(n)
+        helpers.assert_csc_matches(mat, data['particle_hole%d/indptr' % n], data['particle_hole%d/indices' % n],
+                                   data['particle_hole%d/data' % n], rtol=0)
+    with pytest.raises(ValueError):
+        jw_sparse_givens_rotation(0, 2, 1.0, 1.0, 5)
+    with pytest.raises(ValueError):
+        jw_sparse_givens_rotation(4, 5, 1.0, 1.0, 5)
