@@ -273,6 +273,61 @@ def _lanczos_pass(dev_op, start, locked, krylov_dim, tol, bufs, ritz=None, comm=
     return alphas, betas, theta, s, res
 
 
+def _stored_basis_capacity(dev_op, krylov_dim, comm):
+    """Experimental (OFB_LANCZOS_STORE=1, never run on a GPU in round 1): number of Lanczos
+    vectors that can stay in HBM (70 % of the free memory), or 0 to keep the two-pass scheme.
+    One GPU only: the ranks of a sharded solve would have to agree on the number."""
+    import os
+    if os.environ.get('OFB_LANCZOS_STORE') != '1' or comm.world != 1:
+        return 0
+    device = getattr(getattr(dev_op, 'plan', None), 'device', 0)
+    free = ctypes.c_size_t()
+    _lib.call('ofb_device_info', c_int(device), None, None, ctypes.byref(free), None, None)
+    fit = int(0.7 * free.value) // (dev_op.dim * C128)
+    return min(krylov_dim, fit) if fit >= 16 else 0
+
+
+def _lanczos_pass_stored(dev_op, start, locked, steps, tol, bufs, basis, comm=_LOCAL):
+    """One Lanczos sweep that keeps v_0 .. v_{m-1} as the columns of `basis` (steps columns) and
+    forms the Ritz vector y = V s with one pass over the stored vectors instead of replaying the
+    recurrence: m matrix-vector products instead of 2 m - 1.  Same recurrence and stopping rule
+    as _lanczos_pass."""
+    n = dev_op.dim
+
+    def col(k):
+        return basis + k * n * C128
+    copy(n, start, col(0))
+    alphas, betas = [], []
+    beta_prev = 0.0
+    theta, s = None, None
+    for it in range(steps):
+        v = col(it)
+        w = col(it + 1) if it + 1 < steps else bufs['c']
+        dev_op.apply(v, w)
+        if locked:
+            _project_out(n, locked, w, comm)
+        alpha = gdot(n, v, w, comm).real
+        lanczos_update(n, alpha, beta_prev, v, col(it - 1) if it else None, w)
+        beta = gnorm(n, w, comm)
+        alphas.append(alpha)
+        if (it < 32) or (it % 4 == 3) or it == steps - 1:
+            d, e = numpy.array(alphas), numpy.array(betas)
+            vals, vecs = scipy.linalg.eigh_tridiagonal(d, e, select='i', select_range=(0, 0)) \
+                if len(d) > 1 else (d.copy(), numpy.ones((1, 1)))
+            theta, s = float(vals[0]), vecs[:, 0]
+            scale = max(1.0, abs(theta))
+            if abs(beta * s[-1]) <= tol * scale or beta <= 1e-14 * scale:
+                break
+        if it == steps - 1:
+            break
+        betas.append(beta)
+        scal(n, 1.0 / beta, w)
+        beta_prev = beta
+    _lib.call('ofb_memset', c_void_p(bufs['y']), c_int(0), ctypes.c_size_t(n * C128), c_void_p(None))
+    multi_axpy(n, numpy.asarray(s, dtype=numpy.complex128), basis, n, 0.0, bufs['y'])
+    return alphas, betas, theta, s
+
+
 def lanczos_lowest(dev_op, initial_guess=None, locked=(), tol=1e-10, krylov_dim=None,
                    max_restarts=40, seed=1234, comm=_LOCAL, stats=None):
     """Lowest eigenpair of a Hermitian device operator, orthogonal to `locked` vectors.
@@ -294,6 +349,8 @@ def lanczos_lowest(dev_op, initial_guess=None, locked=(), tol=1e-10, krylov_dim=
     else:
         fill_random(n, seed + 104729 * comm.rank, False, start.ptr)
     hy = _lib.DeviceBuffer(n * C128)
+    stored = _stored_basis_capacity(dev_op, krylov_dim, comm)
+    basis = _lib.DeviceBuffer(stored * n * C128) if stored else None
     theta = 0.0
     residual = numpy.inf
     for restart in range(max_restarts):
@@ -304,11 +361,17 @@ def lanczos_lowest(dev_op, initial_guess=None, locked=(), tol=1e-10, krylov_dim=
             fill_random(n, seed + 7919 * (restart + 1) + 104729 * comm.rank, False, start.ptr)
             continue
         scal(n, 1.0 / norm, start.ptr)
-        alphas, betas, theta, s, _ = _lanczos_pass(dev_op, start.ptr, locked, krylov_dim, tol, bufs,
-                                                   comm=comm)
-        _lanczos_pass(dev_op, start.ptr, locked, krylov_dim, tol, bufs, ritz=s, comm=comm)
+        if basis is not None:
+            alphas, betas, theta, s = _lanczos_pass_stored(dev_op, start.ptr, locked, stored, tol, bufs,
+                                                           basis.ptr, comm=comm)
+            applied = len(alphas)
+        else:
+            alphas, betas, theta, s, _ = _lanczos_pass(dev_op, start.ptr, locked, krylov_dim, tol, bufs,
+                                                       comm=comm)
+            _lanczos_pass(dev_op, start.ptr, locked, krylov_dim, tol, bufs, ritz=s, comm=comm)
+            applied = 2 * len(alphas) - 1
         if stats is not None:
-            stats['matvecs'] = stats.get('matvecs', 0) + 2 * len(alphas) - 1 + 1
+            stats['matvecs'] = stats.get('matvecs', 0) + applied + 1
             stats['restarts'] = restart + 1
         y = bufs['y']
         if locked:
@@ -324,6 +387,8 @@ def lanczos_lowest(dev_op, initial_guess=None, locked=(), tol=1e-10, krylov_dim=
     for owner in owners.values():
         owner.free()
     hy.free()
+    if basis is not None:
+        basis.free()
     return theta, start, residual
 
 

@@ -25,6 +25,9 @@ hints)
     done
     python scripts/sector_bench.py hub44_half mol28
     OFB_SUPPORT_HINTS=1 python scripts/sector_bench.py hub44_half mol28
+    # stored-basis Lanczos (OFB_LANCZOS_STORE=1): time to the ground state, sector cases
+    python scripts/sector_bench.py hub44_half --lanczos
+    OFB_LANCZOS_STORE=1 python scripts/sector_bench.py hub44_half --lanczos
     ;;
 ncu)
     # one full capture of the hinted kernel per workload (only after the plain runs above exited 0)

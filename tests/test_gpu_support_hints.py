@@ -112,3 +112,24 @@ def test_sector_kernel_on_the_reduced_table(kind, monkeypatch):
         assert abs(expectation(reduced, v) - e_want) <= 1e-12 * abs(e_want)
         if kind == 'sz_number':
             assert reduced.apply_plan.n_terms < plain.plan.n_terms
+
+
+def test_stored_basis_lanczos_gives_the_same_ground_state(monkeypatch):
+    """OFB_LANCZOS_STORE=1 (linalg/krylov.py:_lanczos_pass_stored): the Krylov vectors stay in HBM and
+    the Ritz vector is one pass over them -- about half the matrix-vector products, same result."""
+    from openfermion_b200.linalg import LinearQubitOperator, SectorLinearQubitOperator, get_ground_state, krylov
+    for build in (lambda: LinearQubitOperator(hamiltonians.hubbard_jw(2, 4), 16),
+                  lambda: LinearQubitOperator(hamiltonians.molecular_jw(6, seed=1234), 12),
+                  lambda: SectorLinearQubitOperator(hamiltonians.hubbard_jw(3, 4), 24, n_electrons=12, sz_value=0.0)):
+        monkeypatch.delenv('OFB_LANCZOS_STORE', raising=False)
+        op = build()
+        stats_two_pass, stats_stored = {}, {}
+        dev = krylov.as_device_operator(op)
+        e_two, vec, res_two = krylov.lanczos_lowest(dev, stats=stats_two_pass)
+        monkeypatch.setenv('OFB_LANCZOS_STORE', '1')
+        e_one, vec1, res_one = krylov.lanczos_lowest(dev, stats=stats_stored)
+        assert abs(e_one - e_two) <= 1e-10 * max(1.0, abs(e_two))
+        assert res_one <= 1e-8 * max(1.0, abs(e_one))
+        assert stats_stored['matvecs'] < 0.7 * stats_two_pass['matvecs']
+        energy, state = get_ground_state(op)
+        assert abs(energy - e_two) <= 1e-10 * max(1.0, abs(e_two))
