@@ -274,11 +274,11 @@ def _lanczos_pass(dev_op, start, locked, krylov_dim, tol, bufs, ritz=None, comm=
 
 
 def _stored_basis_capacity(dev_op, krylov_dim, comm):
-    """Experimental (OFB_LANCZOS_STORE=1, never run on a GPU in round 1): number of Lanczos
-    vectors that can stay in HBM (70 % of the free memory), or 0 to keep the two-pass scheme.
-    One GPU only: the ranks of a sharded solve would have to agree on the number."""
+    """Number of Lanczos vectors that can stay in HBM (70 % of the free memory), or 0 to keep
+    the two-pass scheme (also with OFB_LANCZOS_STORE=0).  One GPU only: the ranks of a sharded
+    solve would have to agree on the number."""
     import os
-    if os.environ.get('OFB_LANCZOS_STORE') != '1' or comm.world != 1:
+    if os.environ.get('OFB_LANCZOS_STORE', '1') != '1' or comm.world != 1:
         return 0
     device = getattr(getattr(dev_op, 'plan', None), 'device', 0)
     free = ctypes.c_size_t()

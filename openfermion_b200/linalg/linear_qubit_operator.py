@@ -165,13 +165,13 @@ class SectorLinearQubitOperator(scipy.sparse.linalg.LinearOperator):
 
     @property
     def apply_plan(self):
-        """The plan the sector matvec / expectation kernels run on.  Experimental
-        (OFB_SUPPORT_HINTS=1, openfermion_b200/support.py): the orbit-reduced term table, for the
-        group conditions that sector membership implies; otherwise the full plan."""
+        """The plan the sector matvec / expectation kernels run on: the orbit-reduced term table
+        (openfermion_b200/support.py) for the group conditions that sector membership implies;
+        the full plan when there are none or with OFB_SUPPORT_HINTS=0."""
         if self._apply_plan is None:
             self._apply_plan = self.plan
             tables = self.sector.tables
-            if os.environ.get('OFB_SUPPORT_HINTS') == '1' and tables is not None:
+            if os.environ.get('OFB_SUPPORT_HINTS', '1') == '1' and tables is not None:
                 from openfermion_b200 import support
                 x, z, c = compile_qubit_operator(self.qubit_operator, self.n_qubits)
                 group_x, mask1, mask2, flags = support.group_conditions(x, z, c)
@@ -179,7 +179,7 @@ class SectorLinearQubitOperator(scipy.sparse.linalg.LinearOperator):
                                                              tables.plus, tables.minus)
                 if numpy.any(flags):
                     xr, zr, cr = support.reduce_terms(x, z, c, group_x, mask1, mask2, flags)
-                    self._apply_plan = PauliPlan(self.n_qubits, xr, zr, cr)
+                    self._apply_plan = PauliPlan(self.n_qubits, xr, zr, cr, hints=False)
         return self._apply_plan
 
     @property

@@ -12,7 +12,7 @@ from openfermion_b200._lib import c_void_p, c_int, c_int64
 class PauliPlan:
     """Compiled Pauli sum: apply / expectation / diagonal / CSC through the C ABI."""
 
-    def __init__(self, n_qubits, x_mask, z_mask, coeff, device=0):
+    def __init__(self, n_qubits, x_mask, z_mask, coeff, device=0, hints=True):
         _lib.require_device()
         self.n_qubits = int(n_qubits)
         self.dim = 1 << self.n_qubits
@@ -30,8 +30,11 @@ class PauliPlan:
         self._read_info()
         self.support_fraction = 1.0
         self._k1_handle = None  # separate plan of the reduced term table (support hints)
-        mode = os.environ.get('OFB_SUPPORT_HINTS')  # experimental: '1' = hints + reduced table, 'hints'
-        if mode in ('1', 'hints') and self.n_qubits <= 32 and len(c):
+        # Support hints (openfermion_b200/support.py) are on by default: K1 / K2 skip the gathers
+        # on which a group's coefficient is structurally zero and run on the orbit-reduced term
+        # table.  OFB_SUPPORT_HINTS=0 turns them off, =hints keeps the full table.
+        mode = os.environ.get('OFB_SUPPORT_HINTS', '1')
+        if mode in ('1', 'hints') and self.n_qubits <= 32 and len(c) and hints:
             self.set_support_hints(x, z, c, reduce=(mode == '1'))
 
     @classmethod
@@ -62,7 +65,7 @@ class PauliPlan:
         self.n_terms, self.n_groups, self.n_diag_terms = t.value, g.value, d.value
 
     def set_support_hints(self, x_mask, z_mask, coeff, reduce=True):
-        """Experimental (openfermion_b200/support.py): tell the kernels where each group's
+        """Support hints (openfermion_b200/support.py): tell the kernels where each group's
         coefficient is structurally zero, so that those gathers are skipped; with reduce=True
         K1/K2 also run on the orbit-reduced term table (one term per symmetry orbit), held in
         a second library plan -- diagonal and CSC keep the full table."""

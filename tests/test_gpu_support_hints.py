@@ -1,8 +1,7 @@
-"""EXPERIMENTAL (not run by default): the support-hint kernel variant
-(k_apply_tile<..., COND = true>, ofb_plan_set_support, openfermion_b200/support.py) was written
-after the round-1 GPU budget was spent and has never run on a GPU.  Enable with
-OFB_TEST_EXPERIMENTAL=1:   OFB_TEST_EXPERIMENTAL=1 python -m pytest tests/test_gpu_support_hints.py -m gpu
-The checks: same H|psi>, expectation and sharded partial applies with and without hints."""
+"""The support-hint kernel variant (k_apply_tile<..., COND = true>, ofb_plan_set_support,
+openfermion_b200/support.py; the default since round 2) against the plain kernel on the full
+term table: same H|psi>, expectation and sharded partial applies with and without hints; the
+sector kernel on the orbit-reduced table; stored-basis Lanczos against the two-pass scheme."""
 import os
 
 import numpy
@@ -11,9 +10,7 @@ import pytest
 import helpers
 from openfermion_b200 import compiler, hamiltonians
 
-pytestmark = [pytest.mark.gpu,
-              pytest.mark.skipif(os.environ.get('OFB_TEST_EXPERIMENTAL') != '1',
-                                 reason='experimental kernel variant, set OFB_TEST_EXPERIMENTAL=1')]
+pytestmark = pytest.mark.gpu
 
 CASES = [
     ('hubbard_2x2_n8_small_state_kernel', lambda: hamiltonians.hubbard_jw(2, 2, 1.0, 4.0, 0.3, 0.2), 8),
@@ -40,8 +37,8 @@ def test_hints_do_not_change_the_result(name, builder, n, reduce):
     from openfermion_b200.plan import PauliPlan
     op = builder()
     x, z, c = compiler.compile_qubit_operator(op, n)
-    plain = PauliPlan(n, x, z, c)
-    hinted = PauliPlan(n, x, z, c)
+    plain = PauliPlan(n, x, z, c, hints=False)
+    hinted = PauliPlan(n, x, z, c, hints=False)
     hinted.set_support_hints(x, z, c, reduce=reduce)
     v = _state(n, 3)
     want = plain.apply_host(v)
@@ -71,8 +68,8 @@ def test_hints_with_shards_and_accumulate():
         basis = ShardBasis.natural(n) if kind == 'natural' else \
             ShardBasis.for_sharding(n, 3, x, local_order='locality')
         xb, zb, cb = basis.transform_terms(x, z, c)
-        plain = PauliPlan(n, xb, zb, cb)
-        hinted = PauliPlan(n, xb, zb, cb)
+        plain = PauliPlan(n, xb, zb, cb, hints=False)
+        hinted = PauliPlan(n, xb, zb, cb, hints=False)
         hinted.set_support_hints(xb, zb, cb)
         layout = ShardLayout(n, world, xb)
         v = basis.from_natural(_state(n, 5))
@@ -94,12 +91,12 @@ def test_hints_with_shards_and_accumulate():
 
 @pytest.mark.parametrize('kind', ['sz_number', 'number'])
 def test_sector_kernel_on_the_reduced_table(kind, monkeypatch):
-    """SectorLinearQubitOperator.apply_plan under OFB_SUPPORT_HINTS=1: the unchanged sector kernel
+    """SectorLinearQubitOperator.apply_plan with support hints (the default): the unchanged sector kernel
     on the orbit-reduced table (only the conditions sector membership implies)."""
     from openfermion_b200.linalg import SectorLinearQubitOperator, expectation
     for op, n in ((hamiltonians.hubbard_jw(2, 4, 1.0, 4.0, 0.3, 0.2), 16), (hamiltonians.molecular_jw(7, seed=4), 14)):
         kwargs = dict(n_electrons=6, sz_value=0.0) if kind == 'sz_number' else dict(n_electrons=5)
-        monkeypatch.delenv('OFB_SUPPORT_HINTS', raising=False)
+        monkeypatch.setenv('OFB_SUPPORT_HINTS', '0')
         plain = SectorLinearQubitOperator(op, n, **kwargs)
         rng = numpy.random.default_rng(1)
         v = rng.normal(size=plain.shape[0]) + 1j * rng.normal(size=plain.shape[0])
@@ -115,13 +112,13 @@ def test_sector_kernel_on_the_reduced_table(kind, monkeypatch):
 
 
 def test_stored_basis_lanczos_gives_the_same_ground_state(monkeypatch):
-    """OFB_LANCZOS_STORE=1 (linalg/krylov.py:_lanczos_pass_stored): the Krylov vectors stay in HBM and
+    """Stored-basis Lanczos (linalg/krylov.py:_lanczos_pass_stored, the default): the Krylov vectors stay in HBM and
     the Ritz vector is one pass over them -- about half the matrix-vector products, same result."""
     from openfermion_b200.linalg import LinearQubitOperator, SectorLinearQubitOperator, get_ground_state, krylov
     for build in (lambda: LinearQubitOperator(hamiltonians.hubbard_jw(2, 4), 16),
                   lambda: LinearQubitOperator(hamiltonians.molecular_jw(6, seed=1234), 12),
                   lambda: SectorLinearQubitOperator(hamiltonians.hubbard_jw(3, 4), 24, n_electrons=12, sz_value=0.0)):
-        monkeypatch.delenv('OFB_LANCZOS_STORE', raising=False)
+        monkeypatch.setenv('OFB_LANCZOS_STORE', '0')
         op = build()
         stats_two_pass, stats_stored = {}, {}
         dev = krylov.as_device_operator(op)
