@@ -247,6 +247,70 @@ int ofb_sector_csc_count(ofb_plan *plan, ofb_sector *sector, int64_t *nnz, int *
 int ofb_sector_csc_fill_host(ofb_plan *plan, ofb_sector *sector, void *h_indptr, void *h_indices,
                              void *h_data, int index_bits);
 
+/* ---- GF(2) relabelling of basis indices (csrc/relabel.cu, openfermion_b200/shard_basis.py) -------
+ * h_cols[b] (b < n_bits <= 40) is the image of index bit b; the image of an index is the XOR of
+ * the images of its set bits.  The reference keeps qubit q at index bit n-1-q
+ * (linalg/linear_qubit_operator.py:78-84); relabelled solves convert on the way in and out.
+ * ofb_vec_fill_random_mapped: element i gets the counter-based random value of index
+ * map(index_base | i) (the generator of ofb_vec_fill_random): a shard of ONE global random state
+ * whatever the sharding or basis.  ofb_vec_relabel: d_out[c] = d_in[map(c)] over 2^n_bits. */
+int ofb_vec_fill_random_mapped(int64_t n, uint64_t seed, int real_only, void *d_x,
+                               uint64_t index_base, int n_bits, const uint64_t *h_cols, void *stream);
+int ofb_vec_relabel(int n_bits, const uint64_t *h_cols, const void *d_in, void *d_out, void *stream);
+
+/* ---- device-resident Lanczos (csrc/krylov.cu) --------------------------------------------------
+ * Replaces the ARPACK call of get_ground_state / get_gap (linalg/sparse_tools.py:578,1090:
+ * eigsh(k=1|2, which='SA')) with a restarted three-term Lanczos whose vectors never leave the
+ * device.  An ofb_linop is a handle on "y = A x" for one device: a compiled plan (K1), a plan
+ * inside a symmetry sector (K7) or a CSR matrix already on the device (ofb_csr_matvec). */
+typedef struct ofb_linop ofb_linop;
+int ofb_linop_from_plan(ofb_plan *plan, ofb_linop **op);
+int ofb_linop_from_sector(ofb_plan *plan, ofb_sector *sector, ofb_linop **op);
+int ofb_linop_from_csr(int64_t n_rows, const void *d_indptr, const void *d_indices,
+                       const void *d_data, int index_bits, int device, ofb_linop **op);
+int ofb_linop_destroy(ofb_linop *op);
+int ofb_linop_dim(const ofb_linop *op, int64_t *dim);
+int ofb_linop_apply(ofb_linop *op, const void *d_in, void *d_out, void *stream);
+/* Lowest eigenpair of a Hermitian operator, orthogonal to the n_locked unit vectors d_locked[]
+ * (get_gap's second state).  d_start: device start vector (any norm) or NULL for a seeded random
+ * one.  Sweeps of at most krylov_dim steps (<= 0: 400) are restarted from the Ritz vector until
+ * the TRUE residual |A y - theta y| <= 10 tol max(1, |theta|); *h_energy is the Rayleigh quotient
+ * of the returned unit vector d_vector (dim complex128).  store_basis != 0: keep the Lanczos
+ * vectors in device memory when they fit (m instead of 2m - 1 applications of A per sweep). */
+int ofb_lanczos_lowest(ofb_linop *op, const void *d_start, int n_locked, const void *const *d_locked,
+                       double tol, int krylov_dim, int max_restarts, uint64_t seed, int store_basis,
+                       double *h_energy, double *h_residual, void *d_vector, int64_t *h_matvecs,
+                       int *h_restarts, void *stream);
+/* Lowest eigenpair of a real symmetric tridiagonal matrix (bisection + inverse iteration, what
+ * scipy.linalg.eigh_tridiagonal(select='i') does through LAPACK): the Ritz problem of a sweep. */
+int ofb_tridiag_lowest(int m, const double *diag, const double *offdiag, double *value,
+                       double *vector);
+/* Per-iteration primitives on UNNORMALISED Lanczos vectors u_k = beta_k v_k, all scalars on the
+ * device (no host synchronisation inside an iteration); the sharded solver
+ * (openfermion_b200/distributed.py) all-reduces scalar slots 0..1 (the dot product) and 2 (the
+ * squared norm) over the ranks between the calls:
+ *   ofb_apply_groups_dot / ofb_kws_dot      slots 0,1 = conj(d_dot) . out  (local part)
+ *   ofb_kws_alpha(k)                        alpha_k = slot0 / beta_k^2 and the update coefficients
+ *   ofb_kws_step                            w <- w/beta_k - (alpha_k/beta_k) u - (beta_k/beta_{k-1}) u_prev
+ *                                           [y += (ritz_k/beta_k) u], slot 2 = local |w|^2
+ *   ofb_kws_beta(k)                         beta_{k+1} = sqrt(slot 2)
+ * replay != 0 repeats a recorded sweep from its stored alpha/beta (Ritz-vector pass). */
+typedef struct ofb_kws ofb_kws;
+int ofb_kws_create(int64_t n_local, int max_steps, int device, ofb_kws **ws);
+int ofb_kws_destroy(ofb_kws *ws);
+int ofb_kws_scalars(ofb_kws *ws, void **d_scalars /* 16 doubles on the device */);
+int ofb_kws_reset(ofb_kws *ws, double beta0, void *stream);
+int ofb_kws_dot(ofb_kws *ws, const void *d_x, const void *d_y, void *stream);
+int ofb_apply_groups_dot(ofb_plan *plan, const void *d_in, void *d_out, int local_bits,
+                         uint64_t index_base, int64_t g_begin, int64_t g_end, int accumulate,
+                         const void *d_dot, ofb_kws *ws, void *stream);
+int ofb_kws_alpha(ofb_kws *ws, int k, int replay, double ritz_k, void *stream);
+int ofb_kws_step(ofb_kws *ws, void *d_w, const void *d_u, const void *d_uprev, void *d_y, int replay,
+                 void *stream);
+int ofb_kws_beta(ofb_kws *ws, int k, void *stream);
+int ofb_kws_fetch(ofb_kws *ws, int count, double *h_alphas, double *h_betas, int *h_flag,
+                  void *stream);
+
 #ifdef __cplusplus
 }
 #endif

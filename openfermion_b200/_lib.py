@@ -101,6 +101,30 @@ SIGNATURES = {
     'ofb_sector_scatter': (c_int, [c_void_p, c_void_p, c_void_p, c_void_p]),
     'ofb_sector_csc_count': (c_int, [c_void_p, c_void_p, P(c_int64), P(c_int), c_void_p]),
     'ofb_sector_csc_fill_host': (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int]),
+    'ofb_vec_fill_random_mapped': (c_int, [c_int64, c_uint64, c_int, c_void_p, c_uint64, c_int, c_void_p,
+                                           c_void_p]),
+    'ofb_vec_relabel': (c_int, [c_int, c_void_p, c_void_p, c_void_p, c_void_p]),
+    'ofb_linop_from_plan': (c_int, [c_void_p, P(c_void_p)]),
+    'ofb_linop_from_sector': (c_int, [c_void_p, c_void_p, P(c_void_p)]),
+    'ofb_linop_from_csr': (c_int, [c_int64, c_void_p, c_void_p, c_void_p, c_int, c_int, P(c_void_p)]),
+    'ofb_linop_destroy': (c_int, [c_void_p]),
+    'ofb_linop_dim': (c_int, [c_void_p, P(c_int64)]),
+    'ofb_linop_apply': (c_int, [c_void_p, c_void_p, c_void_p, c_void_p]),
+    'ofb_lanczos_lowest': (c_int, [c_void_p, c_void_p, c_int, c_void_p, c_double, c_int, c_int,
+                                   c_uint64, c_int, P(c_double), P(c_double), c_void_p, P(c_int64),
+                                   P(c_int), c_void_p]),
+    'ofb_tridiag_lowest': (c_int, [c_int, c_void_p, c_void_p, P(c_double), c_void_p]),
+    'ofb_kws_create': (c_int, [c_int64, c_int, c_int, P(c_void_p)]),
+    'ofb_kws_destroy': (c_int, [c_void_p]),
+    'ofb_kws_scalars': (c_int, [c_void_p, P(c_void_p)]),
+    'ofb_kws_reset': (c_int, [c_void_p, c_double, c_void_p]),
+    'ofb_kws_dot': (c_int, [c_void_p, c_void_p, c_void_p, c_void_p]),
+    'ofb_apply_groups_dot': (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_uint64, c_int64, c_int64,
+                                     c_int, c_void_p, c_void_p, c_void_p]),
+    'ofb_kws_alpha': (c_int, [c_void_p, c_int, c_int, c_double, c_void_p]),
+    'ofb_kws_step': (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_void_p]),
+    'ofb_kws_beta': (c_int, [c_void_p, c_int, c_void_p]),
+    'ofb_kws_fetch': (c_int, [c_void_p, c_int, c_void_p, c_void_p, P(c_int), c_void_p]),
 }
 
 _NO_STATUS = {'ofb_version', 'ofb_last_error', 'ofb_launch_count'}

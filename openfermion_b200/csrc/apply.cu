@@ -30,6 +30,7 @@ constexpr int BLOCK = 1 << OFB_APPLY_BLOCK_BITS;
 constexpr int RT = 1 << CLASS_BITS;  // amplitudes per thread (8, or 16 with OFB_APPLY_CLASS_BITS=4)
 constexpr int TILE = BLOCK * RT;
 constexpr int TILE_BITS = OFB_APPLY_BLOCK_BITS + CLASS_BITS;
+constexpr int HOST_SLABS = 8;  // ofb_apply_host: output slabs copied back while later tiles run
 static_assert(BLOCK == (1 << CLASS_SHIFT), "class bits must sit right above the thread index");
 
 __device__ __forceinline__ double signed_coeff(double c, uint32_t parity) {
@@ -207,17 +208,21 @@ __device__ __forceinline__ void stage_chunk(StageBuf &b, SegCond *sc, const Chun
     cp_async_commit();
 }
 
-template <bool Z32, bool EXPECT, bool HAS_IMAG, bool COND>
+// MODE 0: write H in; 1: fused expectation conj(in) . (H in), no output vector (K2);
+// 2: write H in and the per-tile partial sums of conj(vdot) . (H in) -- the Lanczos alpha for free.
+template <bool Z32, int MODE, bool HAS_IMAG, bool COND>
 __global__ void __launch_bounds__(BLOCK, OFB_APPLY_MIN_CTAS)
 k_apply_tile(const double2 *__restrict__ vin, double2 *__restrict__ vout,
          const Chunk *__restrict__ chunks, uint32_t c0, uint32_t c1,
          const Segment *__restrict__ segs, uint32_t s0, uint32_t s1,
          const TermZC *__restrict__ zc_re, const TermZC *__restrict__ zc_im, int has_imag,
          uint32_t xmask_local, uint64_t index_base, int accumulate, double2 *__restrict__ partials,
-         const SegCond *__restrict__ conds) {
+         const SegCond *__restrict__ conds, uint32_t tile0, const double2 *__restrict__ vdot) {
+    constexpr bool EXPECT = MODE == 1;
     __shared__ StageBuf sbuf[2];
     __shared__ SegCond scond[COND ? 2 : 1][COND ? CHUNK_MAX_SEGS : 1];
-    const uint32_t j0 = blockIdx.x * (uint32_t)TILE + threadIdx.x;  // local index of r = 0
+    const uint32_t tile = blockIdx.x + tile0;  // a launch may cover a slab of the tiles
+    const uint32_t j0 = tile * (uint32_t)TILE + threadIdx.x;  // local index of r = 0
     const uint32_t j_lo = (uint32_t)index_base | j0;
     const uint32_t base_hi = (uint32_t)(index_base >> 32);
 
@@ -292,15 +297,17 @@ k_apply_tile(const double2 *__restrict__ vin, double2 *__restrict__ vout,
         nxt = after;
     }
 
-    if (!EXPECT) {
+    if (MODE != 1) {
 #pragma unroll
         for (int r = 0; r < RT; ++r) vout[(size_t)(j0 + r * BLOCK)] = make_double2(ar[r], ai[r]);
-    } else {
-        // conj(in[j]) * (H in)[j], block-reduced in a fixed order (deterministic)
+    }
+    if (MODE != 0) {
+        // conj(w[j]) * (H in)[j], w = in (expectation) or vdot, block-reduced in a fixed order
+        const double2 *__restrict__ wv = MODE == 1 ? vin : vdot;
         double er = 0.0, ei = 0.0;
 #pragma unroll
         for (int r = 0; r < RT; ++r) {
-            double2 w = vin[(size_t)(j0 + r * BLOCK)];
+            double2 w = wv[(size_t)(j0 + r * BLOCK)];
             er += w.x * ar[r] + w.y * ai[r];
             ei += w.x * ai[r] - w.y * ar[r];
         }
@@ -323,20 +330,21 @@ k_apply_tile(const double2 *__restrict__ vin, double2 *__restrict__ vout,
                 tr += sm[2 * w];
                 ti += sm[2 * w + 1];
             }
-            partials[blockIdx.x] = make_double2(tr, ti);
+            partials[tile] = make_double2(tr, ti);
         }
     }
 }
 
 // Small states (fewer than 2048 local amplitudes): one amplitude per thread, plain sums.
-template <bool EXPECT>
+template <int MODE>
 __global__ void __launch_bounds__(BLOCK)
 k_apply1(const double2 *__restrict__ vin, double2 *__restrict__ vout,
          const Segment *__restrict__ segs, const uint32_t *__restrict__ seg_term_begin,
          uint32_t s0, uint32_t s1,
          const TermZC *__restrict__ zc_re, const TermZC *__restrict__ zc_im, uint32_t dim,
          uint64_t index_base, int accumulate, double2 *__restrict__ partials,
-         const SegCond *__restrict__ conds) {
+         const SegCond *__restrict__ conds, const double2 *__restrict__ vdot) {
+    constexpr bool EXPECT = MODE == 1;
     const uint32_t j = blockIdx.x * BLOCK + threadIdx.x;
     const bool valid = j < dim;
     const uint64_t jz = index_base | j;
@@ -367,12 +375,11 @@ k_apply1(const double2 *__restrict__ vin, double2 *__restrict__ vout,
         ar += sr * v.x - si * v.y;
         ai += sr * v.y + si * v.x;
     }
-    if (!EXPECT) {
-        if (valid) vout[j] = make_double2(ar, ai);
-    } else {
+    if (MODE != 1 && valid) vout[j] = make_double2(ar, ai);
+    if (MODE != 0) {
         double er = 0.0, ei = 0.0;
         if (valid) {
-            double2 w = vin[j];
+            double2 w = MODE == 1 ? vin[j] : vdot[j];
             er = w.x * ar + w.y * ai;
             ei = w.x * ai - w.y * ar;
         }
@@ -426,13 +433,18 @@ static inline uint64_t apply_blocks(int local_bits) {
     return local_bits >= TILE_BITS ? dim / TILE : (dim + BLOCK - 1) / BLOCK;
 }
 
-template <bool EXPECT>
+template <int MODE>
 static int launch_apply_impl(ofb_plan *p, const void *d_in, void *d_out, int local_bits,
                              uint64_t index_base, int64_t g0, int64_t g1, int accumulate,
-                             double2 *partials, cudaStream_t s) {
+                             double2 *partials, cudaStream_t s, uint64_t tile0 = 0,
+                             uint64_t n_tiles = 0, const void *d_dot = nullptr) {
     if (local_bits > 32) return fail(OFB_ERR_INVALID, "more than 2^32 amplitudes per device");
     const uint64_t dim = 1ull << local_bits;
-    const uint64_t blocks = apply_blocks(local_bits);
+    uint64_t blocks = apply_blocks(local_bits);
+    if (n_tiles) {  // a slab of the tiles (tile kernel only)
+        if (local_bits < TILE_BITS || tile0 + n_tiles > blocks) return fail(OFB_ERR_INVALID, "bad tile slab");
+        blocks = n_tiles;
+    }
     const uint32_t s0 = p->h_seg_begin[g0], s1 = p->h_seg_begin[g1];
     if (s1 <= s0) return fail(OFB_ERR_STATE, "empty segment range");
     const uint32_t c0 = p->h_chunk_of_seg[s0], c1 = p->h_chunk_of_seg[s1 - 1] + 1;
@@ -441,9 +453,9 @@ static int launch_apply_impl(ofb_plan *p, const void *d_in, void *d_out, int loc
     if (local_bits >= TILE_BITS) {
         const uint32_t xmask = (uint32_t)(dim - 1);
 #define OFB_GO(ZZ, II, CC)                                                                     \
-    k_apply_tile<ZZ, EXPECT, II, CC><<<(unsigned)blocks, BLOCK, 0, s>>>(                           \
+    k_apply_tile<ZZ, MODE, II, CC><<<(unsigned)blocks, BLOCK, 0, s>>>(                           \
         in, out, p->d_chunks, c0, c1, p->d_segs, s0, s1, p->d_zc, p->d_zc_im, 0, xmask,        \
-        index_base, accumulate, partials, p->d_conds)
+        index_base, accumulate, partials, p->d_conds, (uint32_t)tile0, (const double2 *)d_dot)
         if (p->z_fits32 && p->has_cond) {  // support hints (ofb_plan_set_support), n <= 32 only
             if (p->has_imag) OFB_GO(true, true, true); else OFB_GO(true, false, true);
         } else if (p->z_fits32) {
@@ -453,14 +465,21 @@ static int launch_apply_impl(ofb_plan *p, const void *d_in, void *d_out, int loc
         }
 #undef OFB_GO
     } else {
-        k_apply1<EXPECT><<<(unsigned)blocks, BLOCK, 0, s>>>(in, out, p->d_segs, p->d_seg_term_begin,
+        k_apply1<MODE><<<(unsigned)blocks, BLOCK, 0, s>>>(in, out, p->d_segs, p->d_seg_term_begin,
                                                             s0, s1, p->d_zc, p->d_zc_im,
                                                             (uint32_t)dim, index_base, accumulate,
                                                             partials,
-                                                            (p->has_cond && p->z_fits32) ? p->d_conds : nullptr);
+                                                            (p->has_cond && p->z_fits32) ? p->d_conds : nullptr,
+                                                            (const double2 *)d_dot);
     }
     OFB_LAUNCH_CHECK();
     return OFB_OK;
+}
+
+int launch_apply_slab(ofb_plan *p, const void *d_in, void *d_out, int local_bits, uint64_t tile0,
+                      uint64_t n_tiles, cudaStream_t s) {
+    return launch_apply_impl<0>(p, d_in, d_out, local_bits, 0, 0, p->n_groups, 0, nullptr, s,
+                                tile0, n_tiles);
 }
 
 int launch_apply(ofb_plan *p, const void *d_in, void *d_out, int local_bits, uint64_t index_base,
@@ -473,9 +492,21 @@ int launch_apply(ofb_plan *p, const void *d_in, void *d_out, int local_bits, uin
         }
         return OFB_OK;
     }
-    return launch_apply_impl<false>(p, d_in, d_out, local_bits, index_base, g0, g1, accumulate,
-                                    nullptr, s);
+    return launch_apply_impl<0>(p, d_in, d_out, local_bits, index_base, g0, g1, accumulate,
+                                nullptr, s);
 }
+
+// H in on a group range plus per-block partial sums of conj(d_dot) . (H in) (complete only when
+// this launch finishes the output, i.e. the last launch of an accumulate sequence).
+int launch_apply_dot(ofb_plan *p, const void *d_in, void *d_out, int local_bits, uint64_t index_base,
+                     int64_t g0, int64_t g1, int accumulate, const void *d_dot, double *d_partials,
+                     int64_t *n_partials, cudaStream_t s) {
+    if (g1 <= g0) return fail(OFB_ERR_STATE, "empty group range");
+    *n_partials = (int64_t)apply_blocks(local_bits);
+    return launch_apply_impl<2>(p, d_in, d_out, local_bits, index_base, g0, g1, accumulate,
+                                (double2 *)d_partials, s, 0, 0, d_dot);
+}
+int64_t apply_partial_count(int local_bits) { return (int64_t)apply_blocks(local_bits); }
 
 int launch_expectation(ofb_plan *p, const void *d_state, double *h_out, cudaStream_t s) {
     h_out[0] = h_out[1] = 0.0;
@@ -484,7 +515,7 @@ int launch_expectation(ofb_plan *p, const void *d_state, double *h_out, cudaStre
     const uint64_t blocks = apply_blocks(n);
     int rc = ensure_partials(p, blocks * sizeof(double2) + 16);
     if (rc) return rc;
-    rc = launch_apply_impl<true>(p, d_state, nullptr, n, 0, 0, p->n_groups, 0,
+    rc = launch_apply_impl<1>(p, d_state, nullptr, n, 0, 0, p->n_groups, 0,
                                  (double2 *)p->d_partials, s);
     if (rc) return rc;
     double *d_res = p->d_partials + 2 * blocks;
@@ -558,13 +589,40 @@ int ofb_apply_host(ofb_plan *p, const void *h_in, void *h_out, int ncols) {
     int rc = ensure_stage(p, col_bytes, col_bytes);
     if (rc) return rc;
     cudaStream_t s = 0;
+    // Large states: the output goes back slab by slab on a second stream while the remaining
+    // tiles are still being computed (the input must be complete before the first tile starts:
+    // a gather reaches anywhere).  Host time of the call = H2D + kernel + the last slab's D2H.
+    const uint64_t tiles = p->n_qubits >= TILE_BITS ? dim / TILE : 0;
+    const int slabs = (p->n_groups > 0 && tiles >= 8 * 1024) ? HOST_SLABS : 1;
+    if (slabs > 1 && !p->copy_stream) {
+        OFB_CUDA(cudaStreamCreateWithFlags(&p->copy_stream, cudaStreamNonBlocking));
+        for (int k = 0; k < HOST_SLABS; ++k)
+            OFB_CUDA(cudaEventCreateWithFlags(&p->slab_done[k], cudaEventDisableTiming));
+    }
     for (int c = 0; c < ncols; ++c) {
         OFB_CUDA(cudaMemcpyAsync(p->d_stage_in, (const char *)h_in + c * col_bytes, col_bytes,
                                  cudaMemcpyHostToDevice, s));
-        rc = launch_apply(p, p->d_stage_in, p->d_stage_out, p->n_qubits, 0, 0, p->n_groups, 0, s);
-        if (rc) return rc;
-        OFB_CUDA(cudaMemcpyAsync((char *)h_out + c * col_bytes, p->d_stage_out, col_bytes,
-                                 cudaMemcpyDeviceToHost, s));
+        if (slabs == 1) {
+            rc = launch_apply(p, p->d_stage_in, p->d_stage_out, p->n_qubits, 0, 0, p->n_groups, 0, s);
+            if (rc) return rc;
+            OFB_CUDA(cudaMemcpyAsync((char *)h_out + c * col_bytes, p->d_stage_out, col_bytes,
+                                     cudaMemcpyDeviceToHost, s));
+            continue;
+        }
+        const uint64_t per = tiles / slabs;
+        for (int k = 0; k < slabs; ++k) {  // all launches are queued before the first copy is issued
+            rc = launch_apply_slab(p, p->d_stage_in, p->d_stage_out, p->n_qubits, k * per, per, s);
+            if (rc) return rc;
+            OFB_CUDA(cudaEventRecord(p->slab_done[k], s));
+        }
+        const size_t slab_bytes = col_bytes / slabs;
+        for (int k = 0; k < slabs; ++k) {
+            OFB_CUDA(cudaStreamWaitEvent(p->copy_stream, p->slab_done[k], 0));
+            OFB_CUDA(cudaMemcpyAsync((char *)h_out + c * col_bytes + k * slab_bytes,
+                                     (const char *)p->d_stage_out + k * slab_bytes, slab_bytes,
+                                     cudaMemcpyDeviceToHost, p->copy_stream));
+        }
+        OFB_CUDA(cudaStreamSynchronize(p->copy_stream));  // stage_out is free for the next column
     }
     OFB_CUDA(cudaStreamSynchronize(s));
     return OFB_OK;

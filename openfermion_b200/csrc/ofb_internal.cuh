@@ -162,6 +162,8 @@ struct ofb_plan {
     void *d_stage_in = nullptr;
     void *d_stage_out = nullptr;
     size_t stage_in_bytes = 0, stage_out_bytes = 0;
+    cudaStream_t copy_stream = nullptr;  // ofb_apply_host: slab-wise D2H behind the kernel
+    cudaEvent_t slab_done[8] = {};
 };
 
 namespace ofb {
@@ -170,6 +172,10 @@ int ensure_stage(ofb_plan *plan, size_t in_bytes, size_t out_bytes);
 // launches implemented in apply.cu
 int launch_apply(ofb_plan *plan, const void *d_in, void *d_out, int local_bits, uint64_t index_base,
                  int64_t g0, int64_t g1, int accumulate, cudaStream_t s);
+int launch_apply_dot(ofb_plan *plan, const void *d_in, void *d_out, int local_bits, uint64_t index_base,
+                     int64_t g0, int64_t g1, int accumulate, const void *d_dot, double *d_partials,
+                     int64_t *n_partials, cudaStream_t s);
+int64_t apply_partial_count(int local_bits);
 int launch_expectation(ofb_plan *plan, const void *d_state, double *h_out, cudaStream_t s);
 int launch_diagonal(ofb_plan *plan, double *d_out, cudaStream_t s);
 // csc_exact.cu: scipy-order (std::sort emulation) variants of the two CSC passes

@@ -488,6 +488,9 @@ int ofb_plan_destroy(ofb_plan *p) {
     cudaFree(p->d_stage_in);
     cudaFree(p->d_stage_out);
     if (p->h_pinned_scalars) cudaFreeHost(p->h_pinned_scalars);
+    if (p->copy_stream) cudaStreamDestroy(p->copy_stream);
+    for (cudaEvent_t e : p->slab_done)
+        if (e) cudaEventDestroy(e);
     cudaGetLastError();
     delete p;
     return OFB_OK;

@@ -78,6 +78,27 @@ class ShardLayout:
         return len(self.remote_patterns) * self.local_dim * 16
 
 
+def _splitmix64(z):
+    z = z + numpy.uint64(0x9e3779b97f4a7c15)
+    z = (z ^ (z >> numpy.uint64(30))) * numpy.uint64(0xbf58476d1ce4e5b9)
+    z = (z ^ (z >> numpy.uint64(27))) * numpy.uint64(0x94d049bb133111eb)
+    return z ^ (z >> numpy.uint64(31))
+
+
+def global_random_amplitudes(seed, natural_indices, real_only=False):
+    """Host mirror of the device generator (csrc/vec.cu k_fill_random, csrc/relabel.cu): the
+    unnormalised amplitudes of the seeded global random state at the given natural indices."""
+    g = numpy.asarray(natural_indices, dtype=numpy.uint64)
+    with numpy.errstate(over='ignore'):
+        s = numpy.uint64(seed)
+        a = _splitmix64(s ^ _splitmix64(numpy.uint64(2) * g))
+        b = _splitmix64(s ^ _splitmix64(numpy.uint64(2) * g + numpy.uint64(1)))
+    scale = 1.0 / 9007199254740992.0
+    re = (a >> numpy.uint64(11)).astype(numpy.float64) * scale
+    im = numpy.zeros_like(re) if real_only else (b >> numpy.uint64(11)).astype(numpy.float64) * scale
+    return re + 1j * im
+
+
 class TorchComm:
     """All-reduce hook for the Krylov loops over a torch.distributed group."""
 
@@ -197,14 +218,39 @@ class ShardedPauliOperator:
         import torch
         return torch.cuda.current_stream().cuda_stream if self.dist is not None else None
 
-    def _cuda_apply(self, vin, vout, g_begin, g_end, accumulate):
+    def _cuda_apply(self, vin, vout, g_begin, g_end, accumulate, dot=None):
+        """dot = (ofb_kws handle, vector handle): the launch that completes the output shard also
+        leaves conj(vector) . out in the workspace's scalar slots 0, 1 (ofb_apply_groups_dot)."""
         src = vin if isinstance(vin, int) else vin.ptr
+        if dot is not None and g_end > g_begin:
+            ws, vdot = dot
+            self._lib.call('ofb_apply_groups_dot', self.plan._apply_handle, ctypes.c_void_p(src),
+                           ctypes.c_void_p(vout.ptr), ctypes.c_int(self.layout.local_bits),
+                           ctypes.c_uint64(self.layout.index_base(self.rank)), ctypes.c_int64(g_begin),
+                           ctypes.c_int64(g_end), ctypes.c_int(1 if accumulate else 0),
+                           ctypes.c_void_p(vdot.ptr), ws, ctypes.c_void_p(self._stream()))
+            return
         self.plan.apply_groups_device(src, vout.ptr, self.layout.local_bits,
                                       self.layout.index_base(self.rank), g_begin, g_end,
                                       1 if accumulate else 0, self._stream())
+        if dot is not None:  # empty group range: the output is zero, and so is the dot product
+            ws, vdot = dot
+            self._lib.call('ofb_kws_dot', ws, ctypes.c_void_p(vdot.ptr), ctypes.c_void_p(vout.ptr),
+                           ctypes.c_void_p(self._stream()))
 
     def new_vector(self):
         return self._new()
+
+    def fill_global_random(self, vec, seed, real_only=False):
+        """This rank's shard of the counter-based random state keyed by the NATURAL index
+        (global_random_amplitudes gives the same values on the host): identical for every world
+        size, shard basis and local qubit order."""
+        cols = numpy.zeros(40, dtype=numpy.uint64)
+        cols[:self.n_qubits] = numpy.array(self.basis.cols, dtype=numpy.uint64)
+        self._lib.call('ofb_vec_fill_random_mapped', ctypes.c_int64(self.dim), ctypes.c_uint64(seed),
+                       ctypes.c_int(1 if real_only else 0), ctypes.c_void_p(vec.ptr),
+                       ctypes.c_uint64(self.layout.index_base(self.rank)), ctypes.c_int(self.n_qubits),
+                       self._lib.ptr(cols), ctypes.c_void_p(self._stream()))
 
     def natural_indices(self, rank=None):
         """Natural (reference-order) index of every amplitude of a rank's shard."""
@@ -246,6 +292,24 @@ class ShardedPauliOperator:
                 ptrs.append(p.value)
             self._peer_vectors[vec.ptr] = ptrs
 
+    def unregister_peer_vectors(self, vectors):
+        """Collective: unmap the peers' copies of these vectors and forget them.  MUST run before
+        the vectors are freed -- freeing exported memory while an importer still maps it is
+        undefined, and a later allocation may reuse the address.  Ends with a barrier, after
+        which every rank may free its buffers."""
+        import torch
+        torch.cuda.synchronize()
+        for vec in vectors:
+            ptrs = self._peer_vectors.pop(vec.ptr, None)
+            if ptrs is None:
+                continue
+            for r, p in enumerate(ptrs):
+                if r != self.rank:
+                    self._lib.call('ofb_ipc_close_handle', ctypes.c_void_p(p))
+                    if p in self._opened:
+                        self._opened.remove(p)
+        self.dist.barrier(group=self.group)
+
     def close(self):
         """Unmap the peers' buffers and free this rank's staging shards (call after the last
         matvec has completed on the device)."""
@@ -262,7 +326,13 @@ class ShardedPauliOperator:
         self._staging = []
 
     # -- the sharded matvec --------------------------------------------------------------------
-    def _matvec_ce(self, vin, vout):
+    def _launch(self, src, vout, g0, g1, accumulate, dot=None):
+        if dot is None:
+            self._local_apply(src, vout, g0, g1, accumulate)
+        else:
+            self._local_apply(src, vout, g0, g1, accumulate, dot)
+
+    def _matvec_ce(self, vin, vout, dot=None):
         """Copy-engine pull of the peer shards overlapped with the local groups."""
         lib, layout = self._lib, self.layout
         vp = ctypes.c_void_p
@@ -313,39 +383,41 @@ class ShardedPauliOperator:
         first = True
         if layout.local_pattern is not None:
             _, g0, g1 = layout.local_pattern
-            self._local_apply(vin, vout, g0, g1, False)
+            self._launch(vin, vout, g0, g1, False, None if remote else dot)
             first = False
         for i, (x_hi, g0, g1) in enumerate(remote):
             for event in copied[i % depth]:
                 lib.call('ofb_stream_wait_event', main, event)
-            self._local_apply(self._staging[i % depth], vout, g0, g1, not first)
+            self._launch(self._staging[i % depth], vout, g0, g1, not first,
+                         dot if i == len(remote) - 1 else None)
             first = False
             lib.call('ofb_event_record', consumed[i % depth], main)
             if i + depth < len(remote):
                 post(i + depth)
         if first:
-            self._local_apply(vin, vout, 0, 0, False)
+            self._launch(vin, vout, 0, 0, False, dot)
         return vout
 
-    def matvec(self, vin, vout):
+    def matvec(self, vin, vout, dot=None):
         """vout = (H vin) restricted to this rank's shard.  vin/vout: local shard handles.
         In the 'p2p' and 'ce' modes the caller must make sure (barrier) that every peer has
         finished writing its copy of vin before this call and does not overwrite it before
-        all ranks have completed the call."""
+        all ranks have completed the call.  dot = (ofb_kws, vector): the launch that completes
+        vout also computes the local part of conj(vector) . vout (CUDA path only)."""
         layout = self.layout
         first = True
         if self.mode == 'ce' and layout.remote_patterns:
-            return self._matvec_ce(vin, vout)
+            return self._matvec_ce(vin, vout, dot)
         if self.mode == 'p2p' and layout.remote_patterns:
             ptrs = self._peer_vectors.get(vin.ptr)
             if ptrs is None:
                 raise RuntimeError('p2p mode: vector was not registered with register_peer_vectors')
-            for x_hi, g0, g1 in layout.patterns:
+            for k, (x_hi, g0, g1) in enumerate(layout.patterns):
                 src = vin if x_hi == 0 else ptrs[layout.peer(self.rank, x_hi)]
-                self._local_apply(src, vout, g0, g1, not first)
+                self._launch(src, vout, g0, g1, not first, dot if k == len(layout.patterns) - 1 else None)
                 first = False
             if first:
-                self._local_apply(vin, vout, 0, 0, False)
+                self._launch(vin, vout, 0, 0, False, dot)
             return vout
         remote = layout.remote_patterns
         depth = len(self._staging)
@@ -365,17 +437,18 @@ class ShardedPauliOperator:
             post(i)
         if layout.local_pattern is not None:
             _, g0, g1 = layout.local_pattern
-            self._local_apply(vin, vout, g0, g1, False)
+            self._launch(vin, vout, g0, g1, False, None if remote else dot)
             first = False
         for i, (x_hi, g0, g1) in enumerate(remote):
             for work in works.pop(i):
                 work.wait()
-            self._local_apply(self._staging[i % depth], vout, g0, g1, not first)
+            self._launch(self._staging[i % depth], vout, g0, g1, not first,
+                         dot if i == len(remote) - 1 else None)
             first = False
             if i + depth < len(remote):
                 post(i + depth)  # enqueued after the kernel that still reads this buffer
         if first:
-            self._local_apply(vin, vout, 0, 0, False)
+            self._launch(vin, vout, 0, 0, False, dot)
         return vout
 
     # adapter for krylov.lanczos_lowest: raw pointers in, pointers out
@@ -433,13 +506,15 @@ def init_nccl(local_rank):
 
 def lanczos_ground_state(operator, dist, group=None, tol=1e-10, krylov_dim=None, max_restarts=40,
                          seed=1234, stats=None):
-    """Distributed device-resident Lanczos (same loop as linalg.krylov, reductions over ranks).
-    Returns (energy, local shard of the eigenvector as numpy, residual norm)."""
-    from openfermion_b200.linalg import krylov
-    comm = TorchComm(dist, 'cuda:%d' % operator._device_index(), group)
-    theta, vec, residual = krylov.lanczos_lowest(operator.as_krylov_operator(comm), None, (), tol,
-                                                 krylov_dim, max_restarts, seed, comm, stats)
-    return theta, vec, residual
+    """Distributed device-resident Lanczos: the fused, device-scalar recurrence of csrc/krylov.cu
+    with the two reductions of an iteration all-reduced over the ranks (NCCL, stream-ordered).
+    Returns (energy, device buffer with the local shard of the unit eigenvector, residual norm)."""
+    from openfermion_b200.sharded_lanczos import ShardedLanczos
+    solver = ShardedLanczos(operator, dist, group, max_steps=krylov_dim or 400)
+    try:
+        return solver.solve(tol=tol, max_restarts=max_restarts, seed=seed, stats=stats)
+    finally:
+        solver.close()
 
 
 # ----------------------------------------------------------------------------
@@ -462,7 +537,7 @@ def one_gpu_base(n_qubits):
     return None
 
 
-def bench_main(args, metric, unit, clock_sampler_cls, measured_peak):
+def bench_main(args, metric, unit, clock_sampler_cls, measured_peak, output_check=None):
     import torch
     import torch.distributed as dist
     from openfermion_b200 import _lib, hamiltonians
@@ -489,9 +564,14 @@ def bench_main(args, metric, unit, clock_sampler_cls, measured_peak):
     natural_layout = ShardLayout(n, world, op._natural_x)
     dim_local = op.dim
     vin, vout = op.new_vector(), op.new_vector()
-    krylov.fill_random(dim_local, 42 + rank, False, vin.ptr)
+    # ONE global random state keyed by the natural index: every world size, shard basis and local
+    # qubit order applies H to the same |psi>, so <psi|H|psi> and sampled outputs are comparable
+    # across the --gpus N lines (and with the one-GPU aux measurement of the N = 1 line)
+    state_seed = 42
+    op.fill_global_random(vin, state_seed)
     comm = TorchComm(dist, 'cuda:%d' % local_rank)
-    krylov.scal(dim_local, 1.0 / krylov.gnorm(dim_local, vin.ptr, comm), vin.ptr)
+    state_norm = krylov.gnorm(dim_local, vin.ptr, comm)
+    krylov.scal(dim_local, 1.0 / state_norm, vin.ptr)
     exchanging = mode in ('p2p', 'ce') and bool(layout.remote_patterns)
     if exchanging:
         op.register_peer_vectors([vin])
@@ -583,6 +663,68 @@ def bench_main(args, metric, unit, clock_sampler_cls, measured_peak):
     _lib.call('ofb_host_free', h_in)
     _lib.call('ofb_host_free', h_out)
 
+    # sampled outputs in NATURAL order, gathered on every rank: (H psi)[j] for seeded indices j
+    check = None
+    n_samples = int(getattr(args, 'check_samples', 256))
+    rng = numpy.random.default_rng(11)
+    sample_idx = numpy.unique(rng.integers(0, 1 << n, size=n_samples, dtype=numpy.int64)).astype(numpy.uint64)
+    where = op.basis.to_basis_index(sample_idx)
+    owner = (where >> numpy.uint64(layout.local_bits)).astype(numpy.int64)
+    local_pos = (where & numpy.uint64(dim_local - 1)).astype(numpy.int64)
+    gathered = torch.zeros((len(sample_idx), 2), dtype=torch.float64, device='cuda')
+    host_vals = numpy.zeros((len(sample_idx), 2))
+    one = numpy.zeros(1, dtype=numpy.complex128)
+    for k in numpy.nonzero(owner == rank)[0]:
+        _lib.call('ofb_memcpy_d2h', _lib.ptr(one), vp(vout.ptr + int(local_pos[k]) * 16), ctypes.c_size_t(16), stream)
+        torch.cuda.synchronize()
+        host_vals[k] = (one[0].real, one[0].imag)
+    gathered.copy_(torch.from_numpy(host_vals))
+    dist.all_reduce(gathered)
+    sampled = gathered.cpu().numpy()
+    sampled = sampled[:, 0] + 1j * sampled[:, 1]
+    if rank == 0 and output_check is not None:
+        # the caller's checker (bench.py: the CPU oracle on the reference-order term table) gets
+        # the sampled outputs and a function that evaluates psi at any natural index
+        check = output_check(op_model, n, sample_idx,
+                             lambda idx: global_random_amplitudes(state_seed, idx) / state_norm, sampled)
+    checksum = complex(numpy.sum(sampled))
+
+    # Lanczos: per-iteration time of the device-resident recurrence (config 5), all reductions
+    # included, no host synchronisation inside the timed region
+    lanczos = None
+    lanczos_steps = int(getattr(args, 'lanczos_steps', 20))
+    if lanczos_steps > 0:
+        from openfermion_b200.sharded_lanczos import ShardedLanczos
+        if exchanging:
+            op.unregister_peer_vectors([vin])
+        vin.free()
+        vout.free()
+        warm = 3
+        solver = ShardedLanczos(op, dist, max_steps=lanczos_steps + warm + 1, vectors=3)
+        solver.prepare(seed=state_seed)
+        solver.run(warm)
+        torch.cuda.synchronize()
+        dist.barrier()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        launches1 = _lib.launch_count()
+        a.record()
+        solver.run(lanczos_steps)
+        b.record()
+        torch.cuda.synchronize()
+        dist.barrier()
+        t = torch.tensor([a.elapsed_time(b) / lanczos_steps], dtype=torch.float64, device='cuda')
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        _, _, ritz = solver.history()
+        per_it = float(t.item())
+        lanczos = {'iterations_timed': lanczos_steps, 'warmup_iterations': warm, 'ms_per_iteration': per_it,
+                   'overhead_over_bare_apply': per_it / (ms / args.steps) - 1.0,
+                   'kernel_launches_per_iteration': (_lib.launch_count() - launches1) / float(lanczos_steps),
+                   'lowest_ritz_value_after_%d_iterations' % (lanczos_steps + warm): ritz,
+                   'term_amp_per_s_inside_lanczos': T * float(1 << n) / (per_it / 1e3),
+                   'what': 'H u (alpha fused into the apply launch) + all-reduce(2) + one fused update pass '
+                           '(3 vectors read, 1 written, norm) + all-reduce(1); scalars stay on the device'}
+        solver.close()
+
     if rank == 0:
         dim = float(1 << n)
         seconds = ms / 1e3
@@ -601,9 +743,17 @@ def bench_main(args, metric, unit, clock_sampler_cls, measured_peak):
                        'exchange': mode, 'remote_patterns': len(layout.remote_patterns),
                        'remote_patterns_top_qubit_sharding': len(natural_layout.remote_patterns),
                        'exchange_bytes_per_rank_per_step': layout.exchange_bytes_per_matvec() if mode in ('nccl', 'ce') else None,
-                       'support_hints': os.environ.get('OFB_SUPPORT_HINTS'),  # experimental, None = off
+                       'support_hints': os.environ.get('OFB_SUPPORT_HINTS', '1'),
                        'l2_policy': 'inputs exceed L2 (%.1f GB per shard)' % (dim_local * 16 / 1e9),
-                       'timing': 'CUDA events, max over ranks', 'expectation_check': [e.real, e.imag],
+                       'timing': 'CUDA events, max over ranks',
+                       'state': 'global counter-based random state keyed by the natural index, seed %d, '
+                                'normalised: the same |psi> at every N' % state_seed,
+                       'expectation_value': [e.real, e.imag],
+                       'output_checksum': [checksum.real, checksum.imag],
+                       'self_check_rel_err': check,
+                       'self_check': 'max |(H psi)[j] - oracle| / max |oracle| over %d seeded natural indices j '
+                                     '(oracle: reference-order term sum on the host); bar 1e-12' % len(sample_idx),
+                       'lanczos': lanczos,
                        'one_gpu_same_workload': one_gpu_base(n),
                        'diagnose': diag},
             'clocks': clocks,

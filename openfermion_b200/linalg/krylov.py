@@ -10,6 +10,7 @@ the true residual ||H y - theta y|| is below tolerance.  The returned energy is 
 Rayleigh quotient of the returned vector.
 """
 import ctypes
+import os
 
 import numpy
 import scipy.linalg
@@ -114,6 +115,12 @@ class PlanOperator:
     def apply(self, d_in, d_out, stream=None):
         self.plan.apply_device(d_in, d_out, 1, self.dim, stream)
 
+    def linop(self):
+        """New ofb_linop handle (caller destroys it) for the solvers behind the C ABI."""
+        handle = c_void_p()
+        _lib.call('ofb_linop_from_plan', self.plan._apply_handle, ctypes.byref(handle))
+        return handle
+
 
 class SectorOperator:
     """A compiled Pauli plan restricted to a symmetry sector (K7, csrc/sector.cu)."""
@@ -125,6 +132,11 @@ class SectorOperator:
 
     def apply(self, d_in, d_out, stream=None):
         self.sector.apply_device(self.plan, d_in, d_out, 1, self.dim, stream)
+
+    def linop(self):
+        handle = c_void_p()
+        _lib.call('ofb_linop_from_sector', self.plan.handle, self.sector.handle, ctypes.byref(handle))
+        return handle
 
 
 class CsrOperator:
@@ -145,6 +157,13 @@ class CsrOperator:
         _lib.call('ofb_csr_matvec', c_int64(self.dim), c_void_p(self._indptr.ptr),
                   c_void_p(self._indices.ptr), c_void_p(self._data.ptr), c_int(self.index_bits),
                   c_void_p(d_in), c_void_p(d_out), c_void_p(stream))
+
+    def linop(self):
+        handle = c_void_p()
+        _lib.call('ofb_linop_from_csr', c_int64(self.dim), c_void_p(self._indptr.ptr),
+                  c_void_p(self._indices.ptr), c_void_p(self._data.ptr), c_int(self.index_bits),
+                  c_int(0), ctypes.byref(handle))
+        return handle
 
 
 class HostCallbackOperator:
@@ -328,6 +347,39 @@ def _lanczos_pass_stored(dev_op, start, locked, steps, tol, bufs, basis, comm=_L
     return alphas, betas, theta, s
 
 
+def _lanczos_lowest_native(dev_op, initial_guess, locked, tol, krylov_dim, max_restarts, seed, stats):
+    """ofb_lanczos_lowest (include/ofb200.h): restarted Lanczos on unnormalised vectors with all
+    scalars on the device, one fused update pass per iteration, alpha from the apply kernel."""
+    n = dev_op.dim
+    start = None
+    if initial_guess is not None:
+        guess = numpy.asarray(initial_guess).reshape(-1)
+        if guess.size != n:
+            raise ValueError('initial guess has the wrong dimension')
+        start = _lib.DeviceBuffer(n * C128)
+        upload(guess, start.ptr)
+    out = _lib.DeviceBuffer(n * C128)
+    locked = list(locked)
+    locked_arr = (c_void_p * max(len(locked), 1))(*locked)
+    energy, residual = c_double(), c_double()
+    matvecs, restarts = c_int64(), c_int()
+    store = 1 if os.environ.get('OFB_LANCZOS_STORE', '1') == '1' else 0
+    op = dev_op.linop()
+    try:
+        _lib.call('ofb_lanczos_lowest', op, c_void_p(start.ptr if start else None), c_int(len(locked)),
+                  locked_arr, c_double(tol), c_int(krylov_dim or 0), c_int(max_restarts),
+                  ctypes.c_uint64(seed), c_int(store), ctypes.byref(energy), ctypes.byref(residual),
+                  c_void_p(out.ptr), ctypes.byref(matvecs), ctypes.byref(restarts), c_void_p(None))
+    finally:
+        _lib.call('ofb_linop_destroy', op)
+        if start is not None:
+            start.free()
+    if stats is not None:
+        stats['matvecs'] = stats.get('matvecs', 0) + matvecs.value
+        stats['restarts'] = restarts.value
+    return energy.value, out, residual.value
+
+
 def lanczos_lowest(dev_op, initial_guess=None, locked=(), tol=1e-10, krylov_dim=None,
                    max_restarts=40, seed=1234, comm=_LOCAL, stats=None):
     """Lowest eigenpair of a Hermitian device operator, orthogonal to `locked` vectors.
@@ -335,6 +387,10 @@ def lanczos_lowest(dev_op, initial_guess=None, locked=(), tol=1e-10, krylov_dim=
     Returns (eigenvalue, device buffer holding the unit eigenvector, residual norm).
     """
     n = dev_op.dim
+    if comm.world == 1 and hasattr(dev_op, 'linop') and os.environ.get('OFB_LANCZOS_HOST') != '1':
+        # one device: the whole restarted solver runs behind the C ABI (csrc/krylov.cu)
+        return _lanczos_lowest_native(dev_op, initial_guess, locked, tol, krylov_dim, max_restarts,
+                                      seed, stats)
     if krylov_dim is None:
         krylov_dim = 400
     krylov_dim = max(2, min(krylov_dim, n * comm.world - len(locked)))

@@ -110,13 +110,29 @@ class PauliPlan:
         return numpy.array([self.group(g)[0] for g in range(self.n_groups)], dtype=numpy.uint64)
 
     # ---- host-buffer calls (the ones the drop-in API makes) -------------------
+    # host arrays at least this large are pinned in place (cudaHostRegister) around the call:
+    # pageable copies of a 4.3 GB state run at a fraction of the PCIe rate
+    PIN_THRESHOLD = int(os.environ.get('OFB_PIN_THRESHOLD', str(1 << 26)))
+
     def apply_host(self, columns):
         """columns: complex128, Fortran-contiguous (dim, k) or (dim,) -> same shape."""
         cols = numpy.asarray(columns, dtype=numpy.complex128)
         ncols = 1 if cols.ndim == 1 else cols.shape[1]
         cols = numpy.asfortranarray(cols) if cols.ndim == 2 else numpy.ascontiguousarray(cols)
         out = numpy.empty_like(cols, order='F' if cols.ndim == 2 else 'C')
-        _lib.call('ofb_apply_host', self._apply_handle, _lib.ptr(cols), _lib.ptr(out), c_int(ncols))
+        pinned = []
+        if 0 < self.PIN_THRESHOLD <= cols.nbytes:
+            for array in (cols, out):
+                try:
+                    _lib.call('ofb_host_register', _lib.ptr(array), ctypes.c_size_t(array.nbytes))
+                    pinned.append(array)
+                except _lib.OfbError:  # locked-memory limit, already registered ...: plain copies
+                    pass
+        try:
+            _lib.call('ofb_apply_host', self._apply_handle, _lib.ptr(cols), _lib.ptr(out), c_int(ncols))
+        finally:
+            for array in pinned:
+                _lib.call('ofb_host_unregister', _lib.ptr(array))
         return out
 
     def expectation_host(self, state):

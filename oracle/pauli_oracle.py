@@ -100,6 +100,39 @@ def matvec(terms, n_qubits, x):
     return out.reshape(arr.shape)
 
 
+def matvec_sampled(terms, n_qubits, x, out_indices, chunk=4096):
+    """(H x)[j] for the sampled output indices j only, straight from the reference-order term
+    dict (no grouping, no compiled tables): the scatter form of linear_qubit_operator.py:107-148
+    read backwards,
+
+        out[j] = sum_t coeff_t * i^{y_t} * (-1)^{popc((j ^ x_t) & z_t)} * x[j ^ x_t],
+
+    accumulated in term order.  Cost O(len(terms) * len(out_indices)), independent of 2^n, so it
+    checks a 28-qubit result in seconds.  `x` may be any indexable of length 2^n."""
+    out_indices = numpy.asarray(out_indices, dtype=numpy.uint64)
+    count = len(terms)
+    xm = numpy.zeros(count, dtype=numpy.uint64)
+    zm = numpy.zeros(count, dtype=numpy.uint64)
+    ph = numpy.zeros(count, dtype=complex)
+    for k, (term, coefficient) in enumerate(terms.items()):
+        x_mask, z_mask, y_count = term_masks(term, n_qubits)
+        xm[k], zm[k] = x_mask, z_mask
+        ph[k] = coefficient * _PHASES[y_count % 4]
+    if callable(x):  # amplitudes given as a function of the index (states too large for the host)
+        lookup = lambda index: numpy.asarray(x(index.reshape(-1))).reshape(index.shape)
+    else:
+        vec = numpy.asarray(x).reshape(-1)
+        lookup = lambda index: vec[index.astype(numpy.int64)]
+    out = numpy.zeros(len(out_indices), dtype=complex)
+    for lo in range(0, count, chunk):
+        src = out_indices[:, None] ^ xm[None, lo:lo + chunk]          # the i with i ^ x_t == j
+        signs = 1.0 - 2.0 * bit_parity(src & zm[None, lo:lo + chunk]).astype(numpy.float64)
+        contrib = (signs * ph[None, lo:lo + chunk]) * lookup(src)
+        for k in range(contrib.shape[1]):   # term order, like the reference's accumulation
+            out += contrib[:, k]
+    return out
+
+
 def matmat(terms, n_qubits, X):
     """Column-by-column matvec (scipy LinearOperator._matmat default)."""
     X = numpy.asarray(X)
