@@ -158,6 +158,15 @@ int ofb_csc_count(ofb_plan *plan, int64_t *nnz, int *index_bits, void *stream);
  *           residues that survive eliminate_zeros match the reference bit for bit.
  *           Cost O(T log T) per column.  Must be set before ofb_csc_count. */
 int ofb_plan_set_csc_mode(ofb_plan *plan, int mode);
+/* Signed zeros.  The reference's entries carry the zero signs that scipy.sparse.kron's chain of
+ * complex multiplications leaves behind (sparse_tools.py:160-178: coefficient, identity blocks,
+ * Pauli matrices, one factor per qubit), e.g. (-1.5 + 0i)(1 + 0i) = -1.5 - 0i.  The CSC kernels
+ * replay that chain on a 3-bit state so that `data` matches bit for bit; this host function is
+ * the same replay for one entry (string x_mask / z_mask with coefficient (re, im), column
+ * `column`): *negative = 1 if the zero part of the entry is -0.0, *has_zero = 0 if neither or
+ * both parts are zero (nothing to sign). */
+int ofb_pauli_entry_zero_sign(int n_qubits, uint64_t x_mask, uint64_t z_mask, double re, double im,
+                              uint64_t column, int *has_zero, int *negative);
 int ofb_csc_fill(ofb_plan *plan, void *d_indptr, void *d_indices, void *d_data, int index_bits,
                  void *stream);
 int ofb_csc_fill_host(ofb_plan *plan, void *h_indptr, void *h_indices, void *h_data,

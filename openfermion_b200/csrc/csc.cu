@@ -23,17 +23,17 @@ constexpr int CB = 256;
 
 template <bool Z32>
 __device__ __forceinline__ void group_value(const ScatterRow *__restrict__ rows, uint32_t b,
-                                            uint32_t e, uint64_t c, double &sr, double &si) {
+                                            uint32_t e, uint64_t c, int n, double &sr, double &si) {
     sr = 0.0;
     si = 0.0;
+    bool first = true;  // the sum starts from its first element: 0 + (-0) would lose a signed zero
     for (uint32_t k = b; k < e; ++k) {
         const ScatterRow r = rows[k];
         if ((c & r.occ_mask) == r.occ_val) {
-            uint32_t par = Z32 ? (uint32_t)__popc((uint32_t)c & (uint32_t)r.z)
-                               : (uint32_t)__popcll(c & r.z);
-            uint32_t sgn = par << 31;
-            sr += __hiloint2double(__double2hiint(r.cr) ^ (int)sgn, __double2loint(r.cr));
-            si += __hiloint2double(__double2hiint(r.ci) ^ (int)sgn, __double2loint(r.ci));
+            const double2 v = scatter_value(r, c, n);
+            sr = first ? v.x : sr + v.x;
+            si = first ? v.y : si + v.y;
+            first = false;
         }
     }
 }
@@ -62,7 +62,7 @@ k_csc_count(const ScatterRow *__restrict__ rows, const GroupDesc *__restrict__ g
     for (uint32_t g = 0; g < G; ++g) {
         const GroupDesc gd = groups[g];
         double sr, si;
-        group_value<Z32>(rows, gd.begin, gd.begin + (gd.count & 0x3fffffffu), c, sr, si);
+        group_value<Z32>(rows, gd.begin, gd.begin + (gd.count & 0x3fffffffu), c, n, sr, si);
         if (sr != 0.0 || si != 0.0) {
             uint32_t rank = rank_of(sib, g, n, c ^ gd.x);
             bitmap[(size_t)(rank >> 5) * dim + c] |= 1u << (rank & 31);
@@ -88,7 +88,7 @@ k_csc_fill(const ScatterRow *__restrict__ rows, const GroupDesc *__restrict__ gr
     for (uint32_t g = 0; g < G; ++g) {
         const GroupDesc gd = groups[g];
         double sr, si;
-        group_value<Z32>(rows, gd.begin, gd.begin + (gd.count & 0x3fffffffu), c, sr, si);
+        group_value<Z32>(rows, gd.begin, gd.begin + (gd.count & 0x3fffffffu), c, n, sr, si);
         if (sr != 0.0 || si != 0.0) {
             const uint64_t row = c ^ gd.x;
             uint32_t rank = rank_of(sib, g, n, row);

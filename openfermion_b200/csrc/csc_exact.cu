@@ -21,7 +21,8 @@ __device__ __forceinline__ int64_t build_sorted(const ScatterRow *__restrict__ r
     int64_t m = 0;
     for (uint32_t t = 0; t < T; ++t) {
         const ScatterRow r = rows[t];
-        if ((c & r.occ_mask) == r.occ_val) {
+        // a zero coefficient leaves no triplet in the reference (coo_matrix(0) is empty)
+        if ((c & r.occ_mask) == r.occ_val && (r.cr != 0.0 || r.ci != 0.0)) {
             seq.set(m, ((c ^ r.x) << 32) | t);
             ++m;
         }
@@ -31,11 +32,8 @@ __device__ __forceinline__ int64_t build_sorted(const ScatterRow *__restrict__ r
 }
 
 __device__ __forceinline__ double2 row_value(const ScatterRow *__restrict__ rows, uint32_t t,
-                                             uint64_t c) {
-    const ScatterRow r = rows[t];
-    const int sgn = (int)((uint32_t)__popcll(c & r.z) << 31);
-    return make_double2(__hiloint2double(__double2hiint(r.cr) ^ sgn, __double2loint(r.cr)),
-                        __hiloint2double(__double2hiint(r.ci) ^ sgn, __double2loint(r.ci)));
+                                             uint64_t c, int n) {
+    return scatter_value(rows[t], c, n);  // with the reference's signed zeros (ofb_internal.cuh)
 }
 
 // MODE 0: count non-zero sums; MODE 1: write them.  presorted != 0: the scratch still holds
@@ -45,7 +43,7 @@ __global__ void __launch_bounds__(XB)
 k_csc_exact(const ScatterRow *__restrict__ rows, uint32_t T, uint64_t col0, uint64_t ncols,
             uint64_t *__restrict__ scratch, int64_t batch, int64_t *__restrict__ lens,
             int presorted, int64_t *__restrict__ counts, const int64_t *__restrict__ colptr,
-            I *__restrict__ indices, double2 *__restrict__ data) {
+            I *__restrict__ indices, double2 *__restrict__ data, int n) {
     const uint64_t b = (uint64_t)blockIdx.x * XB + threadIdx.x;
     if (b >= ncols) return;
     const uint64_t c = col0 + b;
@@ -62,12 +60,12 @@ k_csc_exact(const ScatterRow *__restrict__ rows, uint32_t T, uint64_t col0, uint
     while (i < m) {
         const uint64_t e = seq.get(i);
         const uint32_t key = (uint32_t)(e >> 32);
-        double2 acc = row_value(rows, (uint32_t)e, c);
+        double2 acc = row_value(rows, (uint32_t)e, c, n);
         ++i;
         while (i < m) {
             const uint64_t f = seq.get(i);
             if ((uint32_t)(f >> 32) != key) break;
-            const double2 v = row_value(rows, (uint32_t)f, c);
+            const double2 v = row_value(rows, (uint32_t)f, c, n);
             acc.x += v.x;
             acc.y += v.y;
             ++i;
@@ -113,7 +111,7 @@ int csc_exact_count(ofb_plan *p, int64_t *d_counts, cudaStream_t s) {
         const uint64_t ncols = std::min(batch, dim - col0);
         k_csc_exact<0, int32_t><<<(unsigned)((ncols + XB - 1) / XB), XB, 0, s>>>(
             p->d_rows_orig, (uint32_t)p->n_terms, col0, ncols, p->d_sort_scratch, (int64_t)batch, lens,
-            0, d_counts, nullptr, nullptr, nullptr);
+            0, d_counts, nullptr, nullptr, nullptr, p->n_qubits);
         OFB_LAUNCH_CHECK();
     }
     return OFB_OK;
@@ -133,11 +131,11 @@ int csc_exact_fill(ofb_plan *p, const int64_t *d_colptr, void *d_indices, void *
         if (index_bits == 32)
             k_csc_exact<1, int32_t><<<grid, XB, 0, s>>>(
                 p->d_rows_orig, (uint32_t)p->n_terms, col0, ncols, p->d_sort_scratch, (int64_t)batch,
-                lens, presorted, nullptr, d_colptr, (int32_t *)d_indices, (double2 *)d_data);
+                lens, presorted, nullptr, d_colptr, (int32_t *)d_indices, (double2 *)d_data, p->n_qubits);
         else
             k_csc_exact<1, int64_t><<<grid, XB, 0, s>>>(
                 p->d_rows_orig, (uint32_t)p->n_terms, col0, ncols, p->d_sort_scratch, (int64_t)batch,
-                lens, presorted, nullptr, d_colptr, (int64_t *)d_indices, (double2 *)d_data);
+                lens, presorted, nullptr, d_colptr, (int64_t *)d_indices, (double2 *)d_data, p->n_qubits);
         OFB_LAUNCH_CHECK();
     }
     return OFB_OK;

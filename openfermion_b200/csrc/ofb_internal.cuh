@@ -113,7 +113,74 @@ struct __align__(16) ScatterRow {
     uint64_t occ_val;
     uint64_t x;
     double cr, ci;
+    uint64_t flags;  // signed-zero replay, see below
 };
+
+// ---- signed zeros of the reference's matrix entries ----------------------------------------------
+// A matrix entry of qubit_operator_sparse is exact (coefficient times +-1 / +-i), but the SIGN OF
+// ITS ZERO PART is not: scipy.sparse.kron multiplies the running value by one complex factor per
+// qubit (identity blocks, Pauli matrices; linalg/sparse_tools.py:160-178), and IEEE complex
+// multiplication makes (-1.5 + 0i)(1 + 0i) = -1.5 - 0i.  To reproduce the reference's `data`
+// bit for bit the kernels replay that chain on a 3-bit state
+//     bit 2: which part is zero (0: imaginary, 1: real), bit 1: sign of the non-zero part,
+//     bit 0: sign of the zero part,
+// with one transition table per factor value (8 states x 3 bits, generated from numpy's own
+// complex multiplication by oracle/make_golden.py `signed_zero_tables`): E = 1+0i (identity, X,
+// Z on a 0 bit), N = -1+0i (Z on a 1 bit), Y0 = +0+1i / Y1 = -0-1i (Y on a 0 / 1 bit of the column).
+// E is idempotent, so one E per gap between non-E factors equals the reference's identity blocks.
+// Whenever the chain ends in E and starts from a state a Python float or an ordinary complex
+// number produces, the zero part is +0: only strings acting on the LAST qubit need the replay.
+constexpr uint32_t SZ_E = 0xdac680u, SZ_N = 0x937052u, SZ_Y0 = 0x212de4u, SZ_Y1 = 0x48193eu;
+constexpr uint64_t SZ_STATE = 7, SZ_HAS_ZERO = 8, SZ_NEED_REPLAY = 16;
+
+__host__ __device__ inline uint32_t sz_step(uint32_t table, uint32_t state) {
+    return (table >> (3u * state)) & 7u;
+}
+// state after the chain of column c (qubit 0 = index bit n-1 first)
+__host__ __device__ inline uint32_t sz_replay(uint32_t state, uint64_t x, uint64_t z, uint64_t c, int n) {
+    uint64_t active = z & (x | c);  // Y anywhere, Z on a set bit: the factors that are not E
+    int prev = n;
+    while (active) {
+#ifdef __CUDA_ARCH__
+        const int b = 63 - __clzll((long long)active);
+#else
+        const int b = 63 - __builtin_clzll(active);
+#endif
+        if (b < prev - 1) state = sz_step(SZ_E, state);
+        const uint32_t table = ((x >> b) & 1ull) ? (((c >> b) & 1ull) ? SZ_Y1 : SZ_Y0) : SZ_N;
+        state = sz_step(table, state);
+        prev = b;
+        active &= ~(1ull << b);
+    }
+    if (prev > 0) state = sz_step(SZ_E, state);
+    return state;
+}
+// flags of a row from the ORIGINAL coefficient (as numpy sees it) and the string's z mask
+__host__ __device__ inline uint64_t sz_flags(double re, double im, uint64_t z, bool pauli_route) {
+    const bool zr = re == 0.0, zi = im == 0.0;
+    if (zr == zi) return 0;  // both parts non-zero (no zero to sign) or the term is zero
+    if (!pauli_route) return SZ_HAS_ZERO;  // fermion route: sparse products always leave +0
+    const uint32_t sr = re < 0.0 || (zr && 1.0 / re < 0.0), si = im < 0.0 || (zi && 1.0 / im < 0.0);
+    const uint32_t state = zi ? ((sr << 1) | si) : (4u | (si << 1) | sr);
+    const bool ordinary = state != 3u && state != 5u;  // (-a, -0) and (-0, +b) break the shortcut
+    return SZ_HAS_ZERO | state | ((!ordinary || (z & 1ull)) ? SZ_NEED_REPLAY : 0);
+}
+
+#ifdef __CUDACC__
+// value of a scatter row in column c: +-(cr, ci) with the reference's signed zeros
+__device__ __forceinline__ double2 scatter_value(const ScatterRow &r, uint64_t c, int n) {
+    const int sgn = (int)((uint32_t)__popcll(c & r.z) << 31);
+    double re = __hiloint2double(__double2hiint(r.cr) ^ sgn, __double2loint(r.cr));
+    double im = __hiloint2double(__double2hiint(r.ci) ^ sgn, __double2loint(r.ci));
+    if (r.flags & SZ_HAS_ZERO) {
+        uint32_t negative = 0;
+        if (r.flags & SZ_NEED_REPLAY) negative = sz_replay((uint32_t)(r.flags & SZ_STATE), r.x, r.z, c, n) & 1u;
+        const double zero = negative ? -0.0 : 0.0;
+        if (re == 0.0) re = zero; else im = zero;
+    }
+    return make_double2(re, im);
+}
+#endif
 
 }  // namespace ofb
 

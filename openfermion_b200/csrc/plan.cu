@@ -314,7 +314,8 @@ int ofb_plan_create(int n_qubits, int64_t n_terms, const uint64_t *x_mask, const
         mul_neg_i_pow(sre, sim, (4 - (y & 3)) & 3);  // scatter form: coeff * (+i)^y
         gr[k] = re;
         gi[k] = im;
-        rows[k] = ScatterRow{z_mask[t], 0, 0, x_mask[t], sre, sim};
+        rows[k] = ScatterRow{z_mask[t], 0, 0, x_mask[t], sre, sim,
+                             sz_flags(coeff_ri[2 * t], coeff_ri[2 * t + 1], z_mask[t], true)};
     }
     int rc = finish_plan(p, x, order, rows);
     if (rc) {
@@ -456,7 +457,8 @@ int ofb_plan_create_projected(int n_qubits, int64_t n_rows, const uint64_t *occ_
     std::vector<ScatterRow> rows(n_rows);
     for (int64_t k = 0; k < n_rows; ++k) {
         uint32_t t = order[k];
-        rows[k] = ScatterRow{z_mask[t], occ_mask[t], occ_val[t], x_mask[t], coeff_ri[2 * t], coeff_ri[2 * t + 1]};
+        rows[k] = ScatterRow{z_mask[t], occ_mask[t], occ_val[t], x_mask[t], coeff_ri[2 * t], coeff_ri[2 * t + 1],
+                             sz_flags(coeff_ri[2 * t], coeff_ri[2 * t + 1], z_mask[t], false)};
     }
     int rc = finish_plan(p, x, order, rows);
     if (rc) {
@@ -549,6 +551,17 @@ int ofb_plan_set_csc_mode(ofb_plan *p, int mode) {
     if (mode != 0 && mode != 1) return fail(OFB_ERR_INVALID, "csc mode must be 0 or 1");
     p->csc_mode = mode;
     p->csc_nnz = -1;
+    return OFB_OK;
+}
+
+int ofb_pauli_entry_zero_sign(int n_qubits, uint64_t x_mask, uint64_t z_mask, double re, double im,
+                              uint64_t column, int *has_zero, int *negative) {
+    if (!has_zero || !negative || n_qubits < 0 || n_qubits > 40) return fail(OFB_ERR_INVALID, "bad argument");
+    const uint64_t flags = sz_flags(re, im, z_mask, true);
+    *has_zero = (flags & SZ_HAS_ZERO) ? 1 : 0;
+    *negative = 0;
+    if (flags & SZ_NEED_REPLAY)  // the kernels' shortcut: everything else ends in +0
+        *negative = (int)(sz_replay((uint32_t)(flags & SZ_STATE), x_mask, z_mask, column, n_qubits) & 1u);
     return OFB_OK;
 }
 

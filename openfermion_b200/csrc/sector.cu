@@ -403,15 +403,17 @@ k_sector_scatter(SectorDev sec, const double2 *__restrict__ in, double2 *__restr
 
 // ---- sector CSC (scatter form: works for Pauli and for projected fermion rows) ----------
 __device__ __forceinline__ void sector_group_value(const ScatterRow *__restrict__ rows, uint32_t b,
-                                                   uint32_t e, uint64_t c, double &sr, double &si) {
+                                                   uint32_t e, uint64_t c, int n, double &sr, double &si) {
     sr = 0.0;
     si = 0.0;
+    bool first = true;  // as in csc.cu: signed zeros of single-entry sums survive
     for (uint32_t k = b; k < e; ++k) {
         const ScatterRow r = rows[k];
         if ((c & r.occ_mask) == r.occ_val) {
-            const uint32_t sgn = (uint32_t)__popcll(c & r.z) << 31;
-            sr += __hiloint2double(__double2hiint(r.cr) ^ (int)sgn, __double2loint(r.cr));
-            si += __hiloint2double(__double2hiint(r.ci) ^ (int)sgn, __double2loint(r.ci));
+            const double2 v = scatter_value(r, c, n);
+            sr = first ? v.x : sr + v.x;
+            si = first ? v.y : si + v.y;
+            first = false;
         }
     }
 }
@@ -423,7 +425,7 @@ __global__ void __launch_bounds__(SBLOCK)
 k_sector_csc_pass(SectorDev sec, const ScatterRow *__restrict__ rows,
                   const GroupDesc *__restrict__ groups, uint32_t G, int64_t *__restrict__ counts,
                   const int64_t *__restrict__ colptr, int64_t *__restrict__ tmp_rows,
-                  double2 *__restrict__ tmp_vals) {
+                  double2 *__restrict__ tmp_vals, int n_qubits) {
     const int64_t p = (int64_t)blockIdx.x * SBLOCK + threadIdx.x;
     if (p >= sec.dim) return;
     const uint64_t c = sec.basis[p];
@@ -433,7 +435,7 @@ k_sector_csc_pass(SectorDev sec, const ScatterRow *__restrict__ rows,
         const int64_t row = gd.x == 0 ? p : sector_pos(sec, c ^ gd.x);
         if (row < 0) continue;
         double sr, si;
-        sector_group_value(rows, gd.begin, gd.begin + (gd.count & 0x3fffffffu), c, sr, si);
+        sector_group_value(rows, gd.begin, gd.begin + (gd.count & 0x3fffffffu), c, n_qubits, sr, si);
         if (sr != 0.0 || si != 0.0) {
             if (FILL) {
                 tmp_rows[at] = row;
@@ -907,7 +909,8 @@ int ofb_sector_csc_count(ofb_plan *p, ofb_sector *s, int64_t *nnz, int *index_bi
     int64_t *colptr = s->d_colptr, *counts = s->d_colptr + dim + 1;
     if (dim > 0) {
         k_sector_csc_pass<false><<<sector_grid(dim), SBLOCK, 0, st>>>(
-            s->dev, p->d_rows, p->d_groups, (uint32_t)p->n_groups, counts, nullptr, nullptr, nullptr);
+            s->dev, p->d_rows, p->d_groups, (uint32_t)p->n_groups, counts, nullptr, nullptr, nullptr,
+            p->n_qubits);
         OFB_LAUNCH_CHECK();
     }
     k_sector_scan<<<1, 1024, 0, st>>>(counts, dim, colptr);
@@ -948,7 +951,8 @@ int ofb_sector_csc_fill_host(ofb_plan *p, ofb_sector *s, void *h_indptr, void *h
         if (dim > 0 && nnz > 0) {
             k_sector_csc_pass<true><<<sector_grid(dim), SBLOCK>>>(s->dev, p->d_rows, p->d_groups,
                                                                   (uint32_t)p->n_groups, nullptr,
-                                                                  s->d_colptr, tmp_rows, tmp_vals);
+                                                                  s->d_colptr, tmp_rows, tmp_vals,
+                                                                  p->n_qubits);
             g_launches.fetch_add(1);
             const unsigned wgrid = (unsigned)(((size_t)dim * 32 + SBLOCK - 1) / SBLOCK);
             if (index_bits == 32)

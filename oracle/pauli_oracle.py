@@ -211,9 +211,29 @@ def pauli_term_triplets(term, coefficient, n_qubits):
     dim = 1 << n_qubits
     x_mask, z_mask, y_count = term_masks(term, n_qubits)
     col = numpy.arange(dim, dtype=numpy.uint64)
-    signs = 1.0 - 2.0 * bit_parity(col & numpy.uint64(z_mask)).astype(numpy.float64)
-    # kron multiplies exact unit factors (+-1, +-i) into the coefficient
-    data = (complex(coefficient) * _PHASES[y_count % 4]) * signs.astype(complex)
+    # The values are exact (unit factors +-1, +-i), but the SIGNS OF THEIR ZERO PARTS are not a
+    # function of the product alone: scipy.sparse.kron (COO path, `A.data.repeat(B.nnz) * B.data`)
+    # multiplies the running value by one complex factor per list entry -- the coefficient, an
+    # identity block for every gap, each Pauli matrix (sparse_tools.py:160-178) -- and IEEE
+    # complex multiplication turns (-1.5 + 0j) * (1 + 0j) into (-1.5 - 0j).  Replaying the chain
+    # reproduces the reference's data bit for bit, signed zeros included.
+    factors = {'X': numpy.array([1.0, 1.0], dtype=complex),   # CSC order: column 0, column 1
+               'Y': numpy.array([1.0j, -1.0j], dtype=complex),
+               'Z': numpy.array([1.0, -1.0], dtype=complex)}
+    data = numpy.array([coefficient])
+    if data.dtype == object:
+        data = data.astype(complex)
+    tensor_factor = 0
+    for qubit, action in term:
+        if qubit > tensor_factor:
+            data = (data.reshape(-1, 1) * numpy.ones(1 << (qubit - tensor_factor), dtype=complex)).ravel()
+        data = (data.reshape(-1, 1) * factors[action]).ravel()
+        tensor_factor = qubit + 1
+    if tensor_factor < n_qubits or not term:
+        data = (data.reshape(-1, 1) * numpy.ones(1 << (n_qubits - tensor_factor), dtype=complex)).ravel()
+    if coefficient == 0:  # coo_matrix(0) has no stored entry: the Kronecker product is empty
+        empty = numpy.zeros(0)
+        return numpy.zeros(0, dtype=complex), empty, empty
     row = col ^ numpy.uint64(x_mask)
     return data, row.astype(numpy.float64), col.astype(numpy.float64)
 

@@ -85,7 +85,7 @@ def qubit_case_operator(case):
     return qubit_operator_from(case['terms'], case['coeffs'], case['coeff_is_complex'])
 
 
-def assert_csc_matches(got, indptr, indices, data, rtol=1e-12):
+def assert_csc_matches(got, indptr, indices, data, rtol=1e-12, signed_zeros=True):
     """CSC parity bar: indptr/indices bit-exact, values within rtol of max |value|."""
     assert got.shape[0] + 1 == len(indptr)
     assert got.indices.dtype == indices.dtype, (got.indices.dtype, indices.dtype)
@@ -96,6 +96,8 @@ def assert_csc_matches(got, indptr, indices, data, rtol=1e-12):
         scale = numpy.max(numpy.abs(data))
         assert numpy.max(numpy.abs(got.data - data)) <= rtol * scale
         assert got.data.dtype == data.dtype
+        if rtol == 0 and signed_zeros:  # "bit for bit" means the bytes: signed zeros included
+            assert got.data.tobytes() == numpy.ascontiguousarray(data).tobytes(), 'signed zeros differ'
 
 
 def close(got, want, rtol=1e-12):

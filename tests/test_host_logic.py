@@ -323,12 +323,12 @@ def test_gate_matrix_helpers_match_reference():
         mat = jw_sparse_givens_rotation(int(i), int(j), theta, phi, int(n))
         assert mat.format == 'csc' and mat.nnz == 6 * 2 ** (int(n) - 2)
         helpers.assert_csc_matches(mat, data['givens%d/indptr' % k], data['givens%d/indices' % k],
-                                   data['givens%d/data' % k], rtol=0)
+                                   data['givens%d/data' % k], rtol=0, signed_zeros=False)
         assert numpy.array_equal(mat.data, data['givens%d/data' % k])
     for n in (1, 3, 5):
         mat = jw_sparse_particle_hole_transformation_last_mode(n)
         helpers.assert_csc_matches(mat, data['particle_hole%d/indptr' % n], data['particle_hole%d/indices' % n],
-                                   data['particle_hole%d/data' % n], rtol=0)
+                                   data['particle_hole%d/data' % n], rtol=0, signed_zeros=False)
     with pytest.raises(ValueError):
         jw_sparse_givens_rotation(0, 2, 1.0, 1.0, 5)
     with pytest.raises(ValueError):

@@ -1,8 +1,8 @@
 """CSC parity ladder against the REAL reference at the largest sizes it can build here
 (molecular n <= 14, Hubbard n <= 16; tests/golden/csc_ladder_cases.npz,
 written by oracle/make_golden.py csc_ladder): nnz, index width, indptr and indices bit-exact by
-sha256; values within 1e-12 of max |value| on sampled entries (a warning is raised if they are
-not also bit-exact, as the scipy-order mode intends).  Runs last in the suite."""
+sha256; values within 1e-12 of max |value| on sampled entries and, beyond the bar, bit-exact by
+sha256 as well (signed zeros included).  Runs last in the suite."""
 import hashlib
 
 import numpy
@@ -44,11 +44,10 @@ def test_csc_matches_reference_hashes(case):
     assert numpy.max(numpy.abs(mat.data[pos] - case['sample_data'])) <= 1e-12 * scale
     total = float(case['data_abs_sum'])
     assert abs(numpy.abs(mat.data).sum() - total) <= 1e-12 * total
-    # beyond the parity bar (values within 1e-12): the scipy-order mode is expected to reproduce
-    # the values bit for bit; report, do not fail, if a last bit differs at these sizes
-    if _sha(mat.data) != str(case['data_sha256']):
-        import warnings
-        warnings.warn('%s: CSC values differ from the reference in the last bits' % case.name)
+    # beyond the parity bar (values within 1e-12): the scipy-order mode reproduces the reference's
+    # values bit for bit -- summation order (std::sort replay) AND the signs of zero parts (replay
+    # of scipy.sparse.kron's multiplication chain, csrc/ofb_internal.cuh)
+    assert _sha(mat.data) == str(case['data_sha256']), 'CSC values differ from the reference in some bit'
 
 
 # ---- eigenvalue ladder -----------------------------------------------------------------------
