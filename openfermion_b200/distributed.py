@@ -451,40 +451,6 @@ class ShardedPauliOperator:
             self._launch(vin, vout, 0, 0, False, dot)
         return vout
 
-    # adapter for krylov.lanczos_lowest: raw pointers in, pointers out
-    def as_krylov_operator(self, comm=None):
-        """Operator view for the Krylov loops.  In the 'ce' / 'p2p' modes every new input
-        buffer is registered with the peers on first use (a collective: all ranks run the
-        same deterministic loop, so they meet here with corresponding buffers), and a
-        barrier before each application guarantees that the peers have finished writing
-        their shard of the input; the loop's next all-reduce orders the reads against any
-        later overwrite."""
-        op = self
-
-        class _View:
-            def __init__(self, ptr):
-                self.ptr = ptr
-
-        class _Adapter:
-            dim = op.dim
-
-            def __init__(self):
-                self._wrap = {}
-
-            def _vec(self, ptr):
-                if ptr not in self._wrap:
-                    self._wrap[ptr] = _View(ptr)
-                return self._wrap[ptr]
-
-            def apply(self, d_in, d_out, stream=None):
-                vin = self._vec(d_in)
-                if op.mode in ('ce', 'p2p') and op.layout.remote_patterns:
-                    if d_in not in op._peer_vectors:
-                        op.register_peer_vectors([vin])
-                    comm.barrier()
-                op.matvec(vin, self._vec(d_out))
-        return _Adapter()
-
 
 def init_nccl(local_rank):
     """torch.distributed NCCL group whose communication streams have HIGH priority: the

@@ -439,6 +439,27 @@ def jw_get_ground_state_at_particle_number(sparse_operator, particle_number, sz_
     inside the sector (device Lanczos on the sector kernel); `sz_value` narrows the sector
     to fixed S_z as well, and expand=False returns the dim-long sector vector (the 2^n
     expansion of a 32-qubit state is 64 GiB)."""
+    if ops.is_fermion_operator(sparse_operator):
+        # the matrix-free sector kernel runs on Pauli tables; a FermionOperator is assembled
+        # inside the sector from its projected rows (as jw_number_restrict_operator does) and
+        # solved as a sparse matrix
+        n_qubits = count_qubits(sparse_operator)
+        if sz_value is None:
+            restricted = jw_number_restrict_operator(sparse_operator, particle_number, n_qubits)
+            select = jw_number_indices(particle_number, n_qubits)
+        else:
+            restricted = jw_sz_restrict_operator(sparse_operator, sz_value, particle_number, n_qubits)
+            select = jw_sz_indices(sz_value, n_qubits, n_electrons=particle_number)
+        if restricted.shape[0] - 1 <= 1:
+            eigvals, eigvecs = numpy.linalg.eigh(restricted.toarray())
+            energy, state = eigvals[0], eigvecs[:, 0]
+        else:
+            energy, state = get_ground_state(scipy.sparse.csc_matrix(restricted))
+        if not expand:
+            return energy, state
+        expanded = numpy.zeros(2**n_qubits, dtype=complex)
+        expanded[select] = state
+        return energy, expanded
     if _is_symbolic(sparse_operator):
         from openfermion_b200.linalg.linear_qubit_operator import SectorLinearQubitOperator
         restricted = SectorLinearQubitOperator(sparse_operator, n_electrons=particle_number,

@@ -29,14 +29,12 @@ class _TermDict:
     def _add_term(self, key, coefficient):
         # same rule as the reference's += (symbolic_operator.py:433-456): sums whose
         # magnitude falls below EQ_TOLERANCE are removed from the dict
-        if key in self.terms:
-            total = self.terms[key] + coefficient
-            if abs(total) < EQ_TOLERANCE:
-                del self.terms[key]
-            else:
-                self.terms[key] = total
+        # -- whether or not the key was there before: a tiny new term never enters the dict
+        total = self.terms.get(key, 0) + coefficient
+        if abs(total) < EQ_TOLERANCE:
+            self.terms.pop(key, None)
         else:
-            self.terms[key] = coefficient
+            self.terms[key] = total
 
     def __iadd__(self, other):
         if not isinstance(other, type(self)):

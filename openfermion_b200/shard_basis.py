@@ -25,11 +25,13 @@ the natural order to the last bit after `ShardBasis.to_natural`.
 """
 import numpy
 
+from openfermion_b200.hamiltonians import popcount64  # portable (numpy.bitwise_count needs numpy >= 2)
+
 _ONE = numpy.uint64(1)
 
 
 def _parity64(a):
-    return (numpy.bitwise_count(numpy.asarray(a, dtype=numpy.uint64)) & 1).astype(numpy.uint64)
+    return (popcount64(a) & 1).astype(numpy.uint64)
 
 
 def _reduce_gf2(vector, pivots):
@@ -302,8 +304,8 @@ class ShardBasis:
             return x.copy(), z.copy(), coeff.copy()
         xp = self._apply(self.rows, x)
         zp = self._apply(self.cols, z)
-        y = numpy.bitwise_count(x & z).astype(numpy.int64)
-        yp = numpy.bitwise_count(xp & zp).astype(numpy.int64)
+        y = popcount64(x & z)
+        yp = popcount64(xp & zp)
         delta = (y - yp) % 4
         if numpy.any(delta & 1):
             raise AssertionError('relabelling changed the parity of a Y count')

@@ -24,6 +24,8 @@ Hubbard 81 -> 56 ms); OFB_SUPPORT_HINTS=0 turns it off (see DESIGN.md section 4 
 """
 import numpy
 
+from openfermion_b200.hamiltonians import popcount64  # portable (numpy.bitwise_count needs numpy >= 2)
+
 # relative tolerance on "equal coefficients": the strings of one fermionic excitation get their
 # coefficients from the same integrals but possibly through differently ordered sums
 COEFF_RTOL = 8 * numpy.finfo(numpy.float64).eps
@@ -31,7 +33,7 @@ COEFF_RTOL = 8 * numpy.finfo(numpy.float64).eps
 
 def _phased(x, z, c):
     """Gather-form coefficients k_t = c_t (-i)^{|x & z_t|} (what the kernels sum)."""
-    y = numpy.bitwise_count(numpy.asarray(x, dtype=numpy.uint64) & numpy.asarray(z, dtype=numpy.uint64))
+    y = popcount64(numpy.asarray(x, dtype=numpy.uint64) & numpy.asarray(z, dtype=numpy.uint64))
     return numpy.asarray(c, dtype=numpy.complex128) * numpy.array([1, -1j, -1, 1j])[y % 4]
 
 
@@ -193,7 +195,7 @@ def reduce_terms(x, z, c, group_x, mask1, mask2, flags, class_shift=6, class_mas
     xr = numpy.array(out_x, dtype=numpy.uint64)
     zr = numpy.array(out_z, dtype=numpy.uint64)
     kr = numpy.array(out_k, dtype=numpy.complex128)
-    y = numpy.bitwise_count(xr & zr)
+    y = popcount64(xr & zr)
     cr = kr * numpy.array([1, 1j, -1, -1j])[y % 4]  # undo the gather-form phase: c = k (+i)^y
     return xr, zr, cr
 

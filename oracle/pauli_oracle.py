@@ -265,6 +265,34 @@ def qubit_operator_sparse(terms, n_qubits=None):
     return _coo_to_csc(values, rows, cols, dim)
 
 
+def qubit_operator_sparse_columns(terms, n_qubits, columns):
+    """Columns `columns` (ascending) of qubit_operator_sparse(terms, n_qubits) as a
+    (2^n x len(columns)) CSC block, for sizes at which the whole matrix cannot be built on the
+    host (BASELINE.json config 2: 7.4e8 non-zeros).  Same pipeline restricted to the block --
+    triplets term by term (sparse_tools.py:160-186), scipy's coo -> csc (per-column sort, sum of
+    duplicates), eliminate_zeros -- so structure and values are the reference's whenever the
+    sums are exact (dyadic coefficients); zero signs use the closed form, not the kron chain."""
+    columns = numpy.asarray(columns, dtype=numpy.uint64)
+    count = len(terms)
+    xm = numpy.zeros(count, dtype=numpy.uint64)
+    zm = numpy.zeros(count, dtype=numpy.uint64)
+    ph = numpy.zeros(count, dtype=complex)
+    for k, (term, coefficient) in enumerate(terms.items()):
+        x_mask, z_mask, y_count = term_masks(term, n_qubits)
+        xm[k], zm[k] = x_mask, z_mask
+        ph[k] = coefficient * _PHASES[y_count % 4]
+    keep = ph != 0
+    xm, zm, ph = xm[keep], zm[keep], ph[keep]
+    rows = columns[None, :] ^ xm[:, None]
+    signs = 1.0 - 2.0 * bit_parity(columns[None, :] & zm[:, None]).astype(numpy.float64)
+    values = ph[:, None] * signs
+    local = numpy.broadcast_to(numpy.arange(len(columns), dtype=numpy.int64)[None, :], rows.shape)
+    block = scipy.sparse.coo_matrix((values.ravel(), (rows.ravel().astype(numpy.int64), local.ravel())),
+                                    shape=(1 << n_qubits, len(columns))).tocsc(copy=False)
+    block.eliminate_zeros()
+    return block
+
+
 # ----------------------------------------------------------------------------
 # a7: jordan_wigner_sparse (sparse_tools.py:49-133)
 # ----------------------------------------------------------------------------

@@ -31,12 +31,13 @@ def main():
                         ('dense_complex_14', hamiltonians.random_pauli_sum(14, 300, 3, True), 14)):
         rng = numpy.random.default_rng(1)
         full = rng.normal(size=1 << n) + 1j * rng.normal(size=1 << n)
-        combos = (('nccl', 'natural'), ('p2p', 'natural'), ('ce', 'natural'),
-                  ('ce', 'symmetry'), ('nccl', 'symmetry'), ('p2p', 'symmetry'))
+        combos = (('nccl', 'natural', 'natural'), ('p2p', 'natural', 'natural'), ('ce', 'natural', 'natural'),
+                  ('ce', 'symmetry', 'natural'), ('nccl', 'symmetry', 'natural'), ('p2p', 'symmetry', 'natural'),
+                  ('ce', 'symmetry', 'locality'), ('p2p', 'symmetry', 'locality'))
         if quick:
-            combos = (('ce', 'natural'), ('ce', 'symmetry'))
-        for mode, basis in combos:
-            sop = ShardedPauliOperator(op, n, dist=dist, mode=mode, basis=basis,
+            combos = (('ce', 'natural', 'natural'), ('ce', 'symmetry', 'natural'), ('ce', 'symmetry', 'locality'))
+        for mode, basis, order in combos:
+            sop = ShardedPauliOperator(op, n, dist=dist, mode=mode, basis=basis, local_order=order,
                                        max_staging=1 if mode in ('nccl', 'ce') else None)
             ld = sop.dim
             vin, vout = sop.new_vector(), sop.new_vector()
@@ -53,8 +54,8 @@ def main():
                 want = LinearQubitOperator(op, n) * full
                 result = sop.basis.to_natural(numpy.concatenate(gathered))
                 err = numpy.max(numpy.abs(result - want)) / numpy.max(numpy.abs(want))
-                print('%s %s basis=%s world=%d rel_err=%.2e patterns=%d' % (
-                    name, mode, basis, world, err, len(sop.layout.remote_patterns)))
+                print('%s %s basis=%s order=%s world=%d rel_err=%.2e patterns=%d' % (
+                    name, mode, basis, order, world, err, len(sop.layout.remote_patterns)))
                 ok = ok and err < 1e-12
             dist.barrier()
             sop.close()
@@ -62,15 +63,22 @@ def main():
     e1 = None
     if rank == 0:
         e1, _ = get_ground_state(LinearQubitOperator(hub, 16))
-    for mode, basis in ((('ce', 'symmetry'),) if quick else
-                        (('nccl', 'natural'), ('ce', 'natural'), ('ce', 'symmetry'))):
-        sop = ShardedPauliOperator(hub, 16, dist=dist, mode=mode, basis=basis)
-        stats = {}
-        energy, _, residual = lanczos_ground_state(sop, dist, stats=stats)
-        if rank == 0:
-            print('lanczos %s/%s world=%d E=%.12f single-GPU E=%.12f diff=%.2e residual=%.2e matvecs=%d'
-                  % (mode, basis, world, energy, e1, abs(energy - e1), residual, stats.get('matvecs', 0)))
-            ok = ok and abs(energy - e1) < 1e-10
+    for mode, basis, order in ((('ce', 'natural', 'natural'), ('ce', 'symmetry', 'locality')) if quick else
+                               (('nccl', 'natural', 'natural'), ('ce', 'natural', 'natural'),
+                                ('p2p', 'natural', 'natural'), ('ce', 'symmetry', 'natural'),
+                                ('ce', 'symmetry', 'locality'))):
+        sop = ShardedPauliOperator(hub, 16, dist=dist, mode=mode, basis=basis, local_order=order)
+        # two consecutive solves on ONE operator (the first solve's buffers are
+        # unregistered from the peers before they are freed, so the second cannot hit stale maps)
+        for attempt in range(2):
+            stats = {}
+            energy, vec, residual = lanczos_ground_state(sop, dist, stats=stats, seed=1234 + attempt)
+            vec.free()
+            if rank == 0:
+                print('lanczos %s/%s/%s world=%d solve %d E=%.12f single-GPU E=%.12f diff=%.2e residual=%.2e matvecs=%d'
+                      % (mode, basis, order, world, attempt, energy, e1, abs(energy - e1), residual,
+                         stats.get('matvecs', 0)))
+                ok = ok and abs(energy - e1) < 1e-10
         sop.close()
     if rank == 0:
         print('DIST_CHECK', 'PASS' if ok else 'FAIL')
