@@ -335,6 +335,147 @@ k_apply_tile(const double2 *__restrict__ vin, double2 *__restrict__ vout,
     }
 }
 
+// K1b: H applied to several columns at once (scipy's _matmat behind the block Davidson,
+// linalg/davidson.py:249-256).  The sign sums A of a class run depend on the row index only, not
+// on the vector, so they are computed ONCE per thread for a batch of segments, parked in shared
+// memory (a thread reads back only its own slots, so no barrier is needed), and then applied to
+// every column: per (segment, column) a thread issues its 16 gathers and the multiply-adds, the
+// per-term work (LDS + LOP3 + POPC + IMAD + DADD) and the support test are shared by the columns.
+// The accumulators of one column live in registers only while that column is being processed;
+// between batches they rest in the output vector itself (one extra 16-amplitude read-modify-write
+// per column per batch of ~14 segments: < 10 % of the gather traffic).
+constexpr int MB_RUNS = 24;  // class runs per batch
+
+template <bool Z32>
+__device__ __forceinline__ void store_run_sums(const TermZC *tab, uint32_t runs, uint64_t cnts,
+                                               uint32_t j_lo, uint32_t base_hi, double *slot) {
+#pragma unroll 1
+    for (uint32_t k = 0; k < runs; ++k) {
+        const uint32_t cnt = (uint32_t)cnts & 0xffu;
+        slot[k * BLOCK] = run_sum<Z32>(tab, cnt, tab[0], tab[1], j_lo, base_hi);
+        tab += cnt;
+        cnts >>= 8;
+    }
+}
+
+template <bool Z32, bool HAS_IMAG, bool COND>
+__global__ void __launch_bounds__(BLOCK, 4)
+k_apply_multi(const double2 *__restrict__ vin, double2 *__restrict__ vout, int ncols, int64_t ld,
+              const Chunk *__restrict__ chunks, uint32_t c0, uint32_t c1,
+              const Segment *__restrict__ segs, uint32_t s0, uint32_t s1,
+              const TermZC *__restrict__ zc_re, const TermZC *__restrict__ zc_im,
+              uint32_t xmask_local, uint64_t index_base, const SegCond *__restrict__ conds) {
+    __shared__ StageBuf sbuf[2];
+    __shared__ SegCond scond[COND ? 2 : 1][COND ? CHUNK_MAX_SEGS : 1];
+    __shared__ double a_re[MB_RUNS][BLOCK];
+    __shared__ double a_im[HAS_IMAG ? MB_RUNS : 1][BLOCK];
+    __shared__ uint16_t s_need[COND ? CHUNK_MAX_SEGS : 1][BLOCK];
+    const uint32_t tid = threadIdx.x;
+    const uint32_t j0 = blockIdx.x * (uint32_t)TILE + tid;
+    const uint32_t j_lo = (uint32_t)index_base | j0;
+    const uint32_t base_hi = (uint32_t)(index_base >> 32);
+    constexpr uint32_t ALL = (1u << RT) - 1u;
+    bool first_batch = true;
+
+    Chunk cur = chunks[c0];
+    Chunk nxt = (c0 + 1 < c1) ? chunks[c0 + 1] : cur;
+    stage_chunk<COND>(sbuf[0], scond[0], cur, segs, conds, zc_re, zc_im, HAS_IMAG ? 1 : 0);
+    for (uint32_t c = c0; c < c1; ++c) {
+        Chunk after = nxt;
+        if (c + 1 < c1) {
+            stage_chunk<COND>(sbuf[(c + 1 - c0) & 1], scond[COND ? ((c + 1 - c0) & 1) : 0], nxt, segs, conds,
+                              zc_re, zc_im, HAS_IMAG ? 1 : 0);
+            if (c + 2 < c1) after = chunks[c + 2];
+            cp_async_wait<1>();
+        } else {
+            cp_async_wait<0>();
+        }
+        __syncthreads();
+        const StageBuf &b = sbuf[(c - c0) & 1];
+        const uint32_t lo = max(cur.seg_begin, s0), hi = min(cur.seg_begin + cur.seg_count, s1);
+        uint32_t s = lo;
+        while (s < hi) {
+            // batch [s, e): as many segments as fit MB_RUNS class runs
+            uint32_t e = s, total = 0;
+            while (e < hi) {
+                const uint32_t r = b.segs[e - cur.seg_begin].kind_runs & 0xfu;
+                if (e > s && total + r > (uint32_t)MB_RUNS) break;
+                total += r;
+                ++e;
+            }
+            // phase 1: support test and sign sums of this thread's rows, once for all columns
+            uint32_t rb = 0;
+            for (uint32_t q = s; q < e; ++q) {
+                const Segment &sd = b.segs[q - cur.seg_begin];
+                const uint32_t runs = sd.kind_runs & 0xfu, kind = sd.kind_runs >> 30;
+                uint32_t need = ALL;
+                if (COND) {
+                    const SegCond cd = scond[(c - c0) & 1][q - cur.seg_begin];
+                    const uint32_t q1 = ((uint32_t)__popc(j_lo & cd.m1) + cd.v) & 1u;
+                    const uint32_t q2 = ((uint32_t)__popc(j_lo & cd.m2) + (cd.v >> 1)) & 1u;
+                    need = (cd.pat ^ (q1 - 1u)) & ((cd.pat >> 16) ^ (q2 - 1u)) & ALL;
+                    s_need[q - cur.seg_begin][tid] = (uint16_t)need;
+                }
+                if (need) {
+                    if (!HAS_IMAG || kind != KIND_IMAG)
+                        store_run_sums<Z32>(b.re + sd.rel_begin, runs, sd.cnts, j_lo, base_hi, &a_re[rb][tid]);
+                    if (HAS_IMAG && kind != KIND_REAL)
+                        store_run_sums<Z32>(b.im + sd.rel_begin, runs, sd.cnts, j_lo, base_hi, &a_im[rb][tid]);
+                }
+                rb += runs;
+            }
+            // phase 2: every column gathers its amplitudes and takes the sums from shared memory
+            for (int col = 0; col < ncols; ++col) {
+                const double2 *__restrict__ in = vin + (size_t)col * (size_t)ld;
+                double2 *__restrict__ out = vout + (size_t)col * (size_t)ld;
+                double ar[RT], ai[RT];
+                if (first_batch) {
+#pragma unroll
+                    for (int r = 0; r < RT; ++r) ar[r] = ai[r] = 0.0;
+                } else {
+#pragma unroll
+                    for (int r = 0; r < RT; ++r) {
+                        const double2 o = out[(size_t)(j0 + r * BLOCK)];
+                        ar[r] = o.x;
+                        ai[r] = o.y;
+                    }
+                }
+                rb = 0;
+                for (uint32_t q = s; q < e; ++q) {
+                    const Segment &sd = b.segs[q - cur.seg_begin];
+                    const uint32_t runs = sd.kind_runs & 0xfu, kind = sd.kind_runs >> 30;
+                    const uint32_t need = COND ? (uint32_t)s_need[q - cur.seg_begin][tid] : ALL;
+                    if (need) {
+                        const uint32_t jx = j0 ^ (sd.x_lo & xmask_local);
+                        double2 v[RT];
+                        if (!COND || need == ALL)
+                            load_tile(in, jx, v);
+                        else
+                            load_tile_needed(in, jx, need, v);
+                        uint32_t ids = sd.ids;
+#pragma unroll 1
+                        for (uint32_t k = 0; k < runs; ++k) {
+                            if (!HAS_IMAG || kind != KIND_IMAG)
+                                apply_class_dyn<false>(ids & 0xfu, a_re[rb + k][tid], v, ar, ai);
+                            if (HAS_IMAG && kind != KIND_REAL)
+                                apply_class_dyn<true>(ids & 0xfu, a_im[rb + k][tid], v, ar, ai);
+                            ids >>= 4;
+                        }
+                    }
+                    rb += runs;
+                }
+#pragma unroll
+                for (int r = 0; r < RT; ++r) out[(size_t)(j0 + r * BLOCK)] = make_double2(ar[r], ai[r]);
+            }
+            first_batch = false;
+            s = e;
+        }
+        __syncthreads();  // everyone is done with this buffer before it is refilled
+        cur = nxt;
+        nxt = after;
+    }
+}
+
 // Small states (fewer than 2048 local amplitudes): one amplitude per thread, plain sums.
 template <int MODE>
 __global__ void __launch_bounds__(BLOCK)
@@ -508,6 +649,35 @@ int launch_apply_dot(ofb_plan *p, const void *d_in, void *d_out, int local_bits,
 }
 int64_t apply_partial_count(int local_bits) { return (int64_t)apply_blocks(local_bits); }
 
+// K1b: all groups applied to ncols columns `ld` elements apart in one launch (full state only)
+int launch_apply_multi(ofb_plan *p, const void *d_in, void *d_out, int ncols, int64_t ld, cudaStream_t s) {
+    const int n = p->n_qubits;
+    if (n < TILE_BITS || n > 32 || p->n_groups == 0 || ncols < 2)
+        return fail(OFB_ERR_STATE, "launch_apply_multi: unsupported configuration");
+    const uint64_t dim = 1ull << n;
+    const unsigned blocks = (unsigned)(dim / TILE);
+    const uint32_t s0 = 0, s1 = p->h_seg_begin[p->n_groups];
+    const uint32_t c0 = 0, c1 = p->h_chunk_of_seg[s1 - 1] + 1;
+    const uint32_t xmask = (uint32_t)(dim - 1);
+    const double2 *in = (const double2 *)d_in;
+    double2 *out = (double2 *)d_out;
+#define OFB_MULTI(II, CC)                                                                          \
+    k_apply_multi<true, II, CC><<<blocks, BLOCK, 0, s>>>(in, out, ncols, ld, p->d_chunks, c0, c1,    \
+                                                         p->d_segs, s0, s1, p->d_zc, p->d_zc_im,  \
+                                                         xmask, 0ull, p->d_conds)
+    if (p->has_cond) {
+        if (p->has_imag) OFB_MULTI(true, true); else OFB_MULTI(false, true);
+    } else {
+        if (p->has_imag) OFB_MULTI(true, false); else OFB_MULTI(false, false);
+    }
+#undef OFB_MULTI
+    OFB_LAUNCH_CHECK();
+    return OFB_OK;
+}
+static inline bool multi_ok(const ofb_plan *p, int ncols) {
+    return ncols >= 2 && p->n_qubits >= TILE_BITS && p->n_qubits <= 32 && p->n_groups > 0;
+}
+
 int launch_expectation(ofb_plan *p, const void *d_state, double *h_out, cudaStream_t s) {
     h_out[0] = h_out[1] = 0.0;
     if (p->n_groups == 0) return OFB_OK;
@@ -570,6 +740,8 @@ int ofb_apply(ofb_plan *p, const void *d_in, void *d_out, int ncols, int64_t ld,
     if (ncols < 0 || (ncols > 1 && ld < dim)) return fail(OFB_ERR_INVALID, "bad ncols/ld");
     if (d_in == d_out) return fail(OFB_ERR_INVALID, "d_in and d_out must not alias");
     OFB_CUDA(cudaSetDevice(p->device));
+    if (multi_ok(p, ncols))  // K1b: the per-term work is shared by the columns
+        return launch_apply_multi(p, d_in, d_out, ncols, ld, (cudaStream_t)stream);
     for (int c = 0; c < ncols; ++c) {
         const char *in = (const char *)d_in + (size_t)c * ld * 16;
         char *out = (char *)d_out + (size_t)c * ld * 16;
@@ -586,9 +758,34 @@ int ofb_apply_host(ofb_plan *p, const void *h_in, void *h_out, int ncols) {
     OFB_CUDA(cudaSetDevice(p->device));
     const size_t dim = (size_t)1 << p->n_qubits;
     const size_t col_bytes = dim * 16;
-    int rc = ensure_stage(p, col_bytes, col_bytes);
-    if (rc) return rc;
     cudaStream_t s = 0;
+    int rc;
+    if (multi_ok(p, ncols)) {
+        // matmat: batches of up to 8 columns through K1b (as many as fit a quarter of the free
+        // device memory, in and out staged together)
+        size_t free_b = 0, total_b = 0;
+        OFB_CUDA(cudaMemGetInfo(&free_b, &total_b));
+        free_b += p->stage_in_bytes + p->stage_out_bytes;
+        int batch = (int)std::min<size_t>(8, std::max<size_t>(1, free_b / 4 / (2 * col_bytes)));
+        batch = std::min(batch, ncols);
+        if ((rc = ensure_stage(p, (size_t)batch * col_bytes, (size_t)batch * col_bytes))) return rc;
+        for (int c = 0; c < ncols; c += batch) {
+            const int nb = std::min(batch, ncols - c);
+            OFB_CUDA(cudaMemcpyAsync(p->d_stage_in, (const char *)h_in + (size_t)c * col_bytes,
+                                     (size_t)nb * col_bytes, cudaMemcpyHostToDevice, s));
+            if (nb >= 2)
+                rc = launch_apply_multi(p, p->d_stage_in, p->d_stage_out, nb, (int64_t)dim, s);
+            else
+                rc = launch_apply(p, p->d_stage_in, p->d_stage_out, p->n_qubits, 0, 0, p->n_groups, 0, s);
+            if (rc) return rc;
+            OFB_CUDA(cudaMemcpyAsync((char *)h_out + (size_t)c * col_bytes, p->d_stage_out,
+                                     (size_t)nb * col_bytes, cudaMemcpyDeviceToHost, s));
+        }
+        OFB_CUDA(cudaStreamSynchronize(s));
+        return OFB_OK;
+    }
+    rc = ensure_stage(p, col_bytes, col_bytes);
+    if (rc) return rc;
     // Large states: the output goes back slab by slab on a second stream while the remaining
     // tiles are still being computed (the input must be complete before the first tile starts:
     // a gather reaches anywhere).  Host time of the call = H2D + kernel + the last slab's D2H.

@@ -294,8 +294,12 @@ class Davidson:
         """One iteration (davidson.py:223-286) on device blocks."""
         dim = V.dim
         # 1. operator on the new basis columns (the expensive step)
-        for k in range(MV.count, V.count):
-            op.apply(V.col(k), MV.col(k))
+        if V.count - MV.count >= 2 and hasattr(op, 'apply_block'):
+            # several new columns (n_lowest > 1, the initial block): one batched launch (K1b)
+            op.apply_block(V.col(MV.count), MV.col(MV.count), V.count - MV.count, dim)
+        else:
+            for k in range(MV.count, V.count):
+                op.apply(V.col(k), MV.col(k))
         MV.count = V.count
         m = V.count
         # 2. projected matrix guess_v^H guess_mv: numpy.linalg.eigh reads its lower triangle

@@ -115,6 +115,10 @@ class PlanOperator:
     def apply(self, d_in, d_out, stream=None):
         self.plan.apply_device(d_in, d_out, 1, self.dim, stream)
 
+    def apply_block(self, d_in, d_out, ncols, ld, stream=None):
+        """ncols columns `ld` elements apart in one launch (K1b: the per-term work is shared)."""
+        self.plan.apply_device(d_in, d_out, ncols, ld, stream)
+
     def linop(self):
         """New ofb_linop handle (caller destroys it) for the solvers behind the C ABI."""
         handle = c_void_p()
