@@ -230,3 +230,43 @@ def to_host(buf, shape, dtype, byte_offset=0, stream=None):
         call('ofb_memcpy_d2h', ptr(out), buf.at(byte_offset), c_size_t(out.nbytes), c_void_p(stream))
         call('ofb_stream_sync', c_void_p(stream))
     return out
+
+
+def parallel_d2h(pairs, device=0, threads=None, chunk=1 << 27):
+    """Device -> host copies of large results into ordinary (pageable, usually untouched) numpy
+    arrays from several host threads, each on its own stream.  `pairs` = [(host array, device
+    pointer)].  A pageable copy stages through the driver's pinned buffer and the CPU copy out of
+    it -- where the first touch (page fault + zeroing) of every destination page happens -- runs
+    in the calling thread; ctypes releases the GIL, so the threads overlap.  Measured on the
+    B200 box (16 cores): 4 GB into fresh memory 0.85 s from one thread."""
+    import concurrent.futures
+    threads = threads or max(1, min(8, (os.cpu_count() or 2) // 2))
+    jobs = []
+    for host, dev_ptr in pairs:
+        base, nbytes = host.ctypes.data, host.nbytes
+        try:  # transparent huge pages cut the number of first-touch faults by 512 (best effort)
+            aligned = (base + (1 << 21) - 1) & ~((1 << 21) - 1)
+            if nbytes - (aligned - base) >= (1 << 21):
+                ctypes.CDLL(None).madvise(c_void_p(aligned), c_size_t((nbytes - (aligned - base)) & ~((1 << 21) - 1)),
+                                          c_int(14))  # MADV_HUGEPAGE
+        except Exception:
+            pass
+        for off in range(0, nbytes, chunk):
+            jobs.append((base + off, dev_ptr + off, min(chunk, nbytes - off)))
+    if not jobs:
+        return
+    threads = min(threads, len(jobs))
+
+    def work(k):
+        call('ofb_set_device', c_int(device))
+        stream = c_void_p()
+        call('ofb_stream_create', ctypes.byref(stream))
+        try:
+            for dst, src, size in jobs[k::threads]:
+                call('ofb_memcpy_d2h', c_void_p(dst), c_void_p(src), c_size_t(size), stream)
+            call('ofb_stream_sync', stream)
+        finally:
+            call('ofb_stream_destroy', stream)
+
+    with concurrent.futures.ThreadPoolExecutor(threads) as pool:
+        list(pool.map(work, range(threads)))

@@ -22,6 +22,9 @@
 // L1/L2; term tables are staged to shared memory chunk by chunk with cp.async (double buffered).
 // Per (segment, amplitude) this issues 40 % fewer instructions than the 8-amplitude version
 // (the per-term work is shared by twice as many amplitudes) at 12 instead of 16 warps per SM.
+#include <algorithm>
+#include <cstdlib>
+
 #include "ofb_internal.cuh"
 
 namespace ofb {
@@ -674,8 +677,15 @@ int launch_apply_multi(ofb_plan *p, const void *d_in, void *d_out, int ncols, in
     OFB_LAUNCH_CHECK();
     return OFB_OK;
 }
+// Opt-in (OFB_MULTI_APPLY=1): measured on B200 the batched kernel is SLOWER per column than the
+// single-column one (28-qubit molecular: 1.45x at k = 2, 1.61x at k = 4; profiles/r02_multi_bench.jsonl).
+// With the orbit-reduced tables the shared per-term work is under a third of the instructions,
+// and in the single-column kernel it doubles as latency hiding for the 16 gathers it follows; the
+// batched kernel's second phase has nothing to overlap its gathers with at 8 warps per SM.
 static inline bool multi_ok(const ofb_plan *p, int ncols) {
-    return ncols >= 2 && p->n_qubits >= TILE_BITS && p->n_qubits <= 32 && p->n_groups > 0;
+    const char *on = getenv("OFB_MULTI_APPLY");
+    return on && on[0] == '1' && ncols >= 2 && p->n_qubits >= TILE_BITS && p->n_qubits <= 32 &&
+           p->n_groups > 0;
 }
 
 int launch_expectation(ofb_plan *p, const void *d_state, double *h_out, cudaStream_t s) {

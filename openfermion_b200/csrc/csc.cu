@@ -13,6 +13,7 @@
 // prefix counts, so the fill pass places every entry directly at its sorted position.
 // All loops over groups/rows are warp-uniform (table reads are broadcast loads).
 #include <algorithm>
+#include <cstdlib>
 #include <cstring>
 
 #include "ofb_internal.cuh"
@@ -29,7 +30,8 @@ __device__ __forceinline__ void group_value(const ScatterRow *__restrict__ rows,
     bool first = true;  // the sum starts from its first element: 0 + (-0) would lose a signed zero
     for (uint32_t k = b; k < e; ++k) {
         const ScatterRow r = rows[k];
-        if ((c & r.occ_mask) == r.occ_val) {
+        // (a zero coefficient leaves no triplet in the reference: coo_matrix(0) is empty)
+        if ((c & r.occ_mask) == r.occ_val && (r.cr != 0.0 || r.ci != 0.0)) {
             const double2 v = scatter_value(r, c, n);
             sr = first ? v.x : sr + v.x;
             si = first ? v.y : si + v.y;
@@ -198,6 +200,9 @@ int ofb_csc_count(ofb_plan *p, int64_t *nnz, int *index_bits, void *stream) {
     if (p->csc_mode == 1) {
         int rc = csc_exact_count(p, counts, s);
         if (rc) return rc;
+    } else if (csc_tile_ok(p) && !getenv("OFB_CSC_COLUMN_KERNEL")) {
+        int rc = csc_tile_count(p, words, bitmap, prefix, counts, s);  // K4 v2 (csc_tile.cu)
+        if (rc) return rc;
     } else {
         const unsigned grid = (unsigned)((dim + CB - 1) / CB);
         if (p->z_fits32)
@@ -240,7 +245,16 @@ int ofb_csc_fill(ofb_plan *p, void *d_indptr, void *d_indices, void *d_data, int
     const uint32_t *bitmap = p->d_bitmap, *prefix = p->d_bitmap + (size_t)words * dim;
     const unsigned grid = (unsigned)((dim + CB - 1) / CB);
     const unsigned pgrid = (unsigned)((dim + 1 + 255) / 256);
-#define OFB_FILL(ZZ, II)                                                                        \
+    if (p->csc_mode == 0 && p->csc_nnz > 0 && csc_tile_ok(p) && !getenv("OFB_CSC_COLUMN_KERNEL")) {
+        if (index_bits == 32)
+            k_convert_ptr<int32_t><<<pgrid, 256, 0, s>>>(p->d_colptr, (int64_t)dim + 1, (int32_t *)d_indptr);
+        else
+            k_convert_ptr<int64_t><<<pgrid, 256, 0, s>>>(p->d_colptr, (int64_t)dim + 1, (int64_t *)d_indptr);
+        OFB_LAUNCH_CHECK();
+        return csc_tile_fill(p, words, p->d_bitmap, p->d_bitmap + (size_t)words * dim, p->d_colptr,
+                             d_indices, d_data, index_bits, s);
+    }
+#define OFB_FILL(ZZ, II)                                                                       \
     k_csc_fill<ZZ, II><<<grid, CB, 0, s>>>(p->d_rows, p->d_groups, G, p->d_sib, p->n_qubits, dim, \
                                            bitmap, prefix, p->d_colptr, (II *)d_indices,        \
                                            (double2 *)d_data)

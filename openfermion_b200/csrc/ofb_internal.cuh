@@ -216,6 +216,10 @@ struct ofb_plan {
     uint64_t *d_sort_scratch = nullptr;      // exact mode: [n_terms][batch] (row << 32 | term)
     int64_t sort_batch = 0;                  // columns per batch; == 2^n when one batch suffices
     uint32_t *d_sib = nullptr;  // [n_groups][n_qubits] sibling-subtree sizes
+    // tiled CSC passes (csc_tile.cu): group of every segment, groups that need the per-row path
+    uint32_t *d_seg_group = nullptr;
+    uint8_t *d_group_slow = nullptr;
+    std::vector<uint8_t> h_group_slow;
     // CSC state between count and fill
     int64_t *d_colptr = nullptr;   // 2^n + 1 exclusive scan of counts
     uint32_t *d_bitmap = nullptr;  // [words][2^n] rank-ordered non-zero flags
@@ -249,6 +253,12 @@ int launch_diagonal(ofb_plan *plan, double *d_out, cudaStream_t s);
 int csc_exact_count(ofb_plan *plan, int64_t *d_counts, cudaStream_t s);
 int csc_exact_fill(ofb_plan *plan, const int64_t *d_colptr, void *d_indices, void *d_data,
                    int index_bits, cudaStream_t s);
+// csc_tile.cu: tiled count / fill passes for Pauli plans (term tables shared by 1 024 columns)
+bool csc_tile_ok(const ofb_plan *plan);
+int csc_tile_count(ofb_plan *plan, uint32_t words, uint32_t *bitmap, uint32_t *prefix, int64_t *counts,
+                   cudaStream_t s);
+int csc_tile_fill(ofb_plan *plan, uint32_t words, uint32_t *bitmap, uint32_t *prefix,
+                  const int64_t *colptr, void *d_indices, void *d_data, int index_bits, cudaStream_t s);
 // shared reduction helper (vec.cu): sums `count` rows of `width` doubles
 int reduce_partials(const double *d_partials, int64_t count, int width, double *d_out,
                     cudaStream_t s);

@@ -339,6 +339,18 @@ int ofb_plan_create(int n_qubits, int64_t n_terms, const uint64_t *x_mask, const
         }
         uint32_t kind = all_real ? KIND_REAL : (all_imag ? KIND_IMAG : KIND_COMPLEX);
         p->h_group_kind[g] = kind;
+        {
+            // tiled CSC passes (csc_tile.cu): a part that is zero in every term of the group is +0
+            // in the sum unless EVERY non-zero term needs the signed-zero replay; only then the
+            // group takes the per-row path
+            bool slow = kind != KIND_COMPLEX, any = false;
+            for (uint32_t k = b; k < e; ++k) {
+                if (rows[k].cr == 0.0 && rows[k].ci == 0.0) continue;
+                any = true;
+                if (!(rows[k].flags & SZ_NEED_REPLAY)) slow = false;
+            }
+            p->h_group_slow.push_back((slow && any) ? 1 : 0);
+        }
         p->h_seg_begin[g] = (uint32_t)segs.size();
         idx.resize(e - b);
         std::iota(idx.begin(), idx.end(), b);
@@ -383,7 +395,8 @@ int ofb_plan_create(int n_qubits, int64_t n_terms, const uint64_t *x_mask, const
                 zc_re.push_back(TermZC{z_mask[order[k]], gr[k]});
                 zc_im.push_back(TermZC{z_mask[order[k]], gi[k]});
             }
-            sd.kind_runs = runs | ((uint32_t)(end - pos) << 8) | (kind << 30);
+            // bits 0..3 class runs, bit 4 last segment of its group, 8..23 terms, 30..31 kind
+            sd.kind_runs = runs | ((end == idx.size() ? 1u : 0u) << 4) | ((uint32_t)(end - pos) << 8) | (kind << 30);
             sd.cnts = cnts;
             sd.ids = ids;
             segs.push_back(sd);
@@ -484,6 +497,8 @@ int ofb_plan_destroy(ofb_plan *p) {
     cudaFree(p->d_rows_orig);
     cudaFree(p->d_sort_scratch);
     cudaFree(p->d_sib);
+    cudaFree(p->d_seg_group);
+    cudaFree(p->d_group_slow);
     cudaFree(p->d_colptr);
     cudaFree(p->d_bitmap);
     cudaFree(p->d_partials);

@@ -148,6 +148,8 @@ class PauliPlan:
         _lib.call('ofb_diagonal_host', self.handle, _lib.ptr(out))
         return out
 
+    # CSC outputs at least this large leave the device through _lib.parallel_d2h
+    PARALLEL_D2H_BYTES = int(os.environ.get('OFB_PARALLEL_D2H_BYTES', str(1 << 30)))
     # term-order sums are bit-identical to the reference up to this many triplets per column
     # (libstdc++'s std::sort is a stable insertion sort up to 16 elements)
     STABLE_SORT_LIMIT = 16
@@ -179,8 +181,25 @@ class PauliPlan:
         indptr = numpy.empty(self.dim + 1, dtype=idx_dtype)
         indices = numpy.empty(nnz.value, dtype=idx_dtype)
         data = numpy.empty(nnz.value, dtype=numpy.complex128)
-        _lib.call('ofb_csc_fill_host', self.handle, _lib.ptr(indptr), _lib.ptr(indices),
-                  _lib.ptr(data), bits)
+        if indices.nbytes + data.nbytes >= self.PARALLEL_D2H_BYTES:
+            # gigabytes of output (config 2: 15 GB): fill on the device, then copy out from
+            # several host threads -- a single pageable copy into fresh memory runs at ~5 GB/s
+            # because the first touch of every destination page happens inside it
+            d_indptr = _lib.DeviceBuffer(indptr.nbytes)
+            d_indices = _lib.DeviceBuffer(indices.nbytes)
+            d_data = _lib.DeviceBuffer(data.nbytes)
+            try:
+                _lib.call('ofb_csc_fill', self.handle, c_void_p(d_indptr.ptr), c_void_p(d_indices.ptr),
+                          c_void_p(d_data.ptr), bits, c_void_p(None))
+                _lib.call('ofb_device_sync')
+                _lib.parallel_d2h([(indptr, d_indptr.ptr), (indices, d_indices.ptr), (data, d_data.ptr)],
+                                  device=self.device)
+            finally:
+                for buf in (d_indptr, d_indices, d_data):
+                    buf.free()
+        else:
+            _lib.call('ofb_csc_fill_host', self.handle, _lib.ptr(indptr), _lib.ptr(indices),
+                      _lib.ptr(data), bits)
         if nnz.value == 0:
             # With no terms at all the reference concatenates only its empty float seed lists
             # and returns a float64 matrix; with terms that cancel it stays complex128

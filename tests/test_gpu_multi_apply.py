@@ -28,6 +28,13 @@ def _columns(n, k, seed):
     return numpy.asfortranarray(rng.normal(size=(1 << n, k)) + 1j * rng.normal(size=(1 << n, k)))
 
 
+@pytest.fixture(autouse=True)
+def _batched_kernel_on(monkeypatch):
+    # K1b is opt-in (measured slower per column than the single-column kernel):
+    # these tests keep it correct
+    monkeypatch.setenv('OFB_MULTI_APPLY', '1')
+
+
 @pytest.mark.parametrize('hints', [True, False], ids=['hints', 'plain'])
 @pytest.mark.parametrize('name,builder,n', CASES, ids=[c[0] for c in CASES])
 def test_matmat_matches_oracle_and_single_column_kernel(name, builder, n, hints):
@@ -43,7 +50,13 @@ def test_matmat_matches_oracle_and_single_column_kernel(name, builder, n, hints)
             want = po.matmat(op.terms, n, cols)
             assert helpers.close(got, want, 1e-12)
         single = numpy.stack([plan.apply_host(numpy.ascontiguousarray(cols[:, j])) for j in range(k)], axis=1)
-        assert numpy.array_equal(got, single), 'batched and single-column kernels differ'
+        phased = c * numpy.array([1, -1j, -1, 1j])[hamiltonians.popcount64(x & z) % 4]
+        if numpy.any(phased.imag != 0):
+            # complex phased coefficients: the single-column kernel runs a segment's real table,
+            # then its imaginary table; the batched one alternates per class run (last-bit order)
+            assert helpers.close(got, single, 1e-14)
+        else:
+            assert numpy.array_equal(got, single), 'batched and single-column kernels differ'
 
 
 def test_device_block_apply_with_leading_dimension():
