@@ -181,7 +181,11 @@ int ofb_csr_matvec(int64_t n_rows, const void *d_indptr, const void *d_indices, 
 /* ---- K5: vector kernels for the device-resident Krylov loops
  * (numpy calls in linalg/davidson.py:257-339,439-469 and ARPACK internals behind
  * linalg/sparse_tools.py:578).  All vectors complex128 of length n. Scalars that
- * come back are written to host memory after a stream synchronise. */
+ * come back are written to host memory after a stream synchronise.
+ * Threading: the reductions (dotc, nrm2, maxabs, multi_dotc, davidson_correction) share ONE
+ * scratch buffer and one pinned result buffer per device; call them from one host thread and
+ * one stream at a time per device (as a numpy caller of the reference would: its matvec is
+ * single-threaded).  The plan / sector reductions (expectation) are per object, same rule. */
 int ofb_vec_dotc(int64_t n, const void *d_x, const void *d_y, double *h_out_ri, void *stream);
 int ofb_vec_nrm2(int64_t n, const void *d_x, double *h_out, void *stream);
 int ofb_vec_maxabs(int64_t n, const void *d_x, double *h_out, void *stream);
