@@ -490,16 +490,16 @@ def one_gpu_base(n_qubits):
     """One-GPU measurement of the same Hubbard workload (profiles/sweep_r01.jsonl), so that the
     strong-scaling base of a --gpus N line is explicit (the N = 1 bench line is a different
     workload: BASELINE.json quotes the metric at 28 qubits on 1 GPU and 32 qubits on 2/4/8)."""
-    path = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), 'profiles',
-                        'sweep_r01.jsonl')
-    try:
-        for raw in open(path):
-            rec = json.loads(raw)
-            if rec.get('n_qubits') == n_qubits and rec.get('workload', '').startswith('hubbard'):
-                return {'ms_per_step': rec['ms_per_matvec'], 'value': rec['term_amp_per_s'],
-                        'source': 'profiles/sweep_r01.jsonl'}
-    except Exception:
-        pass
+    profiles = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), 'profiles')
+    for name in ('one_gpu_hubbard32_r02.json', 'sweep_r01.jsonl'):  # newest record first
+        try:
+            for raw in open(os.path.join(profiles, name)):
+                rec = json.loads(raw)
+                if rec.get('n_qubits') == n_qubits and rec.get('workload', '').startswith('hubbard'):
+                    return {'ms_per_step': rec['ms_per_matvec'], 'value': rec['term_amp_per_s'],
+                            'source': rec.get('source', 'profiles/' + name)}
+        except Exception:
+            pass
     return None
 
 
