@@ -260,6 +260,26 @@ int ofb_sector_csc_count(ofb_plan *plan, ofb_sector *sector, int64_t *nnz, int *
 int ofb_sector_csc_fill_host(ofb_plan *plan, ofb_sector *sector, void *h_indptr, void *h_indices,
                              void *h_data, int index_bits);
 
+/* ---- N3: fermion-to-qubit term generation on the device (csrc/termgen.cu) ----------------------
+ * Replaces the symbolic products of transforms/opconversions/jordan_wigner.py:132-331 and
+ * bravyi_kitaev.py:242-337 for operators given as ladder-operator products.  An encoding is four
+ * per-mode mask tables: a_j^(dagger) = 1/2 (A_j -/+ i B_j) with A_j = P(xa[j], za[j]),
+ * B_j = P(xb[j], zb[j]) (qubit-space masks, bit q = qubit q; Jordan-Wigner and Bravyi-Kitaev
+ * tables come from openfermion_b200/hamiltonians.py).  ofb_termgen_add expands
+ * sum_t coeff[t] prod_j ladder(modes[t][j], kind j) -- k factors per term, bit j of kinds_mask = 1
+ * for a raising operator -- into its 2^k strings per term; ofb_termgen_collect merges equal
+ * strings (stable sort + sequential sums: the host builder's summation order, bit-identical
+ * coefficients), drops |sum| < tol (the reference's 1e-8 rule, symbolic_operator.py __iadd__) and
+ * leaves the strings sorted by (x, z); ofb_termgen_fetch copies them out. */
+typedef struct ofb_termgen ofb_termgen;
+int ofb_termgen_create(int n_qubits, const uint64_t *xa, const uint64_t *za, const uint64_t *xb,
+                       const uint64_t *zb, int device, ofb_termgen **gen);
+int ofb_termgen_add(ofb_termgen *gen, int k, uint32_t kinds_mask, int64_t n_terms,
+                    const int32_t *h_modes /* n_terms * k */, const double *h_coeff_ri /* 2 n_terms */);
+int ofb_termgen_collect(ofb_termgen *gen, double tol, int64_t *n_out);
+int ofb_termgen_fetch(ofb_termgen *gen, uint64_t *h_x, uint64_t *h_z, double *h_coeff_ri);
+int ofb_termgen_destroy(ofb_termgen *gen);
+
 /* ---- GF(2) relabelling of basis indices (csrc/relabel.cu, openfermion_b200/shard_basis.py) -------
  * h_cols[b] (b < n_bits <= 40) is the image of index bit b; the image of an index is the XOR of
  * the images of its set bits.  The reference keeps qubit q at index bit n-1-q

@@ -101,6 +101,11 @@ SIGNATURES = {
     'ofb_sector_scatter': (c_int, [c_void_p, c_void_p, c_void_p, c_void_p]),
     'ofb_sector_csc_count': (c_int, [c_void_p, c_void_p, P(c_int64), P(c_int), c_void_p]),
     'ofb_sector_csc_fill_host': (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int]),
+    'ofb_termgen_create': (c_int, [c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_int, P(c_void_p)]),
+    'ofb_termgen_add': (c_int, [c_void_p, c_int, ctypes.c_uint32, c_int64, c_void_p, c_void_p]),
+    'ofb_termgen_collect': (c_int, [c_void_p, c_double, P(c_int64)]),
+    'ofb_termgen_fetch': (c_int, [c_void_p, c_void_p, c_void_p, c_void_p]),
+    'ofb_termgen_destroy': (c_int, [c_void_p]),
     'ofb_pauli_entry_zero_sign': (c_int, [c_int, c_uint64, c_uint64, c_double, c_double, c_uint64,
                                           P(c_int), P(c_int)]),
     'ofb_vec_fill_random_mapped':(c_int, [c_int64, c_uint64, c_int, c_void_p, c_uint64, c_int, c_void_p,

@@ -209,6 +209,43 @@ def _collect(n_qubits, pieces, tol=EQ_TOLERANCE):
     return MaskOperator(n_qubits, ux[keep], uz[keep], total[keep])
 
 
+def _build(n_qubits, specs, tables, device=False, tol=EQ_TOLERANCE):
+    """MaskOperator of a list of ladder-product pieces [(modes (T, k), kinds, coeffs)].
+
+    device=False: numpy expansion + merge on the host (ladder_products, _collect).
+    device=True: the same expansion, merge and 1e-8 rule on the GPU (csrc/termgen.cu, SURVEY.md
+    section 8f row N3): one thread per (term, choice), stable radix sort, sequential run sums in
+    the host builder's order -- the two give identical arrays."""
+    if not device:
+        return _collect(n_qubits, [ladder_products(m, kinds, c, tables) for m, kinds, c in specs], tol)
+    import ctypes
+    from openfermion_b200 import _lib
+    _lib.require_device()
+    if n_qubits > 64:
+        raise ValueError('generators support at most 64 qubits')
+    xa, za, xb, zb = (numpy.ascontiguousarray(t, dtype=numpy.uint64) for t in tables)
+    gen = ctypes.c_void_p()
+    _lib.call('ofb_termgen_create', ctypes.c_int(n_qubits), _lib.ptr(xa), _lib.ptr(za), _lib.ptr(xb),
+              _lib.ptr(zb), ctypes.c_int(0), ctypes.byref(gen))
+    try:
+        for modes, kinds, coeffs in specs:
+            coeffs = numpy.ascontiguousarray(coeffs, dtype=numpy.complex128)
+            modes = numpy.ascontiguousarray(numpy.asarray(modes, dtype=numpy.int32).reshape(len(coeffs), -1))
+            k = len(kinds)
+            mask = sum(1 << j for j, kind in enumerate(kinds) if kind)
+            _lib.call('ofb_termgen_add', gen, ctypes.c_int(k), ctypes.c_uint32(mask),
+                      ctypes.c_int64(len(coeffs)), _lib.ptr(modes) if k else None, _lib.ptr(coeffs))
+        count = ctypes.c_int64()
+        _lib.call('ofb_termgen_collect', gen, ctypes.c_double(tol), ctypes.byref(count))
+        x = numpy.empty(count.value, dtype=numpy.uint64)
+        z = numpy.empty(count.value, dtype=numpy.uint64)
+        c = numpy.empty(count.value, dtype=numpy.complex128)
+        _lib.call('ofb_termgen_fetch', gen, _lib.ptr(x), _lib.ptr(z), _lib.ptr(c))
+    finally:
+        _lib.call('ofb_termgen_destroy', gen)
+    return MaskOperator(n_qubits, x, z, c)
+
+
 # ----------------------------------------------------------------------------
 # Fermi-Hubbard (hamiltonians/hubbard.py:128-179, spinful, up = 2*site, down = 2*site + 1)
 # ----------------------------------------------------------------------------
@@ -261,25 +298,27 @@ def _tables_for(encoding, n_qubits):
     raise ValueError('encoding must be jw or bk')
 
 
-def _jw_of_term_list(term_list, n_qubits, encoding='jw'):
+def _jw_of_term_list(term_list, n_qubits, encoding='jw', device=False):
     tables = _tables_for(encoding, n_qubits)
     by_kind = {}
     for modes, kinds, coefficient in term_list:
         by_kind.setdefault(kinds, ([], []))
         by_kind[kinds][0].append(modes)
         by_kind[kinds][1].append(coefficient)
-    pieces = [ladder_products(m, kinds, c, tables) for kinds, (m, c) in by_kind.items()]
-    return _collect(n_qubits, pieces)
+    specs = [(numpy.asarray(m, dtype=numpy.int64).reshape(len(c), -1), kinds, c)
+             for kinds, (m, c) in by_kind.items()]
+    return _build(n_qubits, specs, tables, device)
 
 
 def hubbard_jw(x_dimension, y_dimension, tunneling=1.0, coulomb=4.0, chemical_potential=0.0,
-               magnetic_field=0.0, periodic=True, encoding='jw'):
+               magnetic_field=0.0, periodic=True, encoding='jw', device=False):
     """jordan_wigner(fermi_hubbard(x, y, t, U)) as a MaskOperator (2*x*y qubits);
-    encoding='bk' gives bravyi_kitaev(...) instead."""
+    encoding='bk' gives bravyi_kitaev(...) instead; device=True expands and merges the strings on
+    the GPU (csrc/termgen.cu)."""
     n_qubits = 2 * x_dimension * y_dimension
     terms = hubbard_fermion_terms(x_dimension, y_dimension, tunneling, coulomb, chemical_potential,
                                   magnetic_field, periodic)
-    return _jw_of_term_list(terms, n_qubits, encoding)
+    return _jw_of_term_list(terms, n_qubits, encoding, device)
 
 
 # ----------------------------------------------------------------------------
@@ -327,33 +366,34 @@ def random_interaction_tensors(n_orbitals, seed=None, dyadic_bits=None):
     return constant, one_spin, two_spin
 
 
-def interaction_operator_jw(constant, one_body, two_body, encoding='jw', n_qubits=None):
+def interaction_operator_jw(constant, one_body, two_body, encoding='jw', n_qubits=None, device=False):
     """JW of constant + sum h_pq p^ q + sum h_pqrs p^ q^ r s (InteractionOperator convention,
-    ops/representations/interaction_operator.py) as a MaskOperator."""
+    ops/representations/interaction_operator.py) as a MaskOperator; device=True expands and merges
+    the strings on the GPU (csrc/termgen.cu, same arrays)."""
     one_body = numpy.asarray(one_body)
     two_body = numpy.asarray(two_body)
     if n_qubits is None:
         n_qubits = one_body.shape[0]
     tables = _tables_for(encoding, n_qubits)
-    pieces = []
-    if constant:
-        pieces.append((numpy.zeros(1, numpy.uint64), numpy.zeros(1, numpy.uint64),
-                       numpy.array([constant], dtype=numpy.complex128)))
+    specs = []
+    if constant:  # the identity string: a product of zero ladder operators
+        specs.append((numpy.zeros((1, 0), dtype=numpy.int64), (), numpy.array([constant], dtype=numpy.complex128)))
     idx1 = numpy.argwhere(one_body != 0)
     if len(idx1):
-        pieces.append(ladder_products(idx1, (1, 0), one_body[tuple(idx1.T)], tables))
+        specs.append((idx1, (1, 0), one_body[tuple(idx1.T)]))
     idx2 = numpy.argwhere(two_body != 0)
     if len(idx2):
-        pieces.append(ladder_products(idx2, (1, 1, 0, 0), two_body[tuple(idx2.T)], tables))
-    return _collect(n_qubits, pieces)
+        specs.append((idx2, (1, 1, 0, 0), two_body[tuple(idx2.T)]))
+    return _build(n_qubits, specs, tables, device)
 
 
-def molecular_jw(n_orbitals, seed=1234, dyadic_bits=None, encoding='jw'):
+def molecular_jw(n_orbitals, seed=1234, dyadic_bits=None, encoding='jw', device=False):
     """The synthetic molecular-type qubit Hamiltonian of BASELINE.json (2*n_orbitals qubits):
     jordan_wigner(random_interaction_operator(n_orbitals, expand_spin=True, real=True, seed));
-    encoding='bk' applies bravyi_kitaev to the same fermion operator."""
+    encoding='bk' applies bravyi_kitaev to the same fermion operator; device=True generates the
+    term table on the GPU (csrc/termgen.cu)."""
     return interaction_operator_jw(*random_interaction_tensors(n_orbitals, seed, dyadic_bits),
-                                   encoding=encoding)
+                                   encoding=encoding, device=device)
 
 
 def random_pauli_sum(n_qubits, n_terms, seed=0, complex_coefficients=False):

@@ -31,7 +31,7 @@ def _count_modes(operator):
     return ops.count_qubits(operator)
 
 
-def _transform(operator, n_qubits, encoding):
+def _transform(operator, n_qubits, encoding, device=False):
     names = {c.__name__ for c in type(operator).__mro__}
     if hasattr(operator, 'one_body_tensor') and hasattr(operator, 'two_body_tensor'):
         needed = numpy.asarray(operator.one_body_tensor).shape[0]
@@ -39,7 +39,7 @@ def _transform(operator, n_qubits, encoding):
             raise ValueError('Invalid number of qubits specified.')
         return hamiltonians.interaction_operator_jw(operator.constant, operator.one_body_tensor,
                                                     operator.two_body_tensor, encoding=encoding,
-                                                    n_qubits=n_qubits)
+                                                    n_qubits=n_qubits, device=device)
     if 'DiagonalCoulombHamiltonian' in names or (
             all(hasattr(operator, a) for a in ('one_body', 'two_body', 'constant'))
             and not hasattr(operator, 'terms')):
@@ -53,16 +53,18 @@ def _transform(operator, n_qubits, encoding):
         n_qubits = needed
     if n_qubits < needed:
         raise ValueError('Invalid number of qubits specified.')
-    return hamiltonians._jw_of_term_list(_fermion_term_list(operator), n_qubits, encoding)
+    return hamiltonians._jw_of_term_list(_fermion_term_list(operator), n_qubits, encoding, device)
 
 
-def jordan_wigner(operator):
+def jordan_wigner(operator, device=False):
     """Jordan-Wigner image of a FermionOperator / InteractionOperator-like tensor object /
-    DiagonalCoulombHamiltonian-like object (jordan_wigner.py:23-65) as a MaskOperator."""
-    return _transform(operator, None, 'jw')
+    DiagonalCoulombHamiltonian-like object (jordan_wigner.py:23-65) as a MaskOperator.
+    device=True expands the ladder products and merges equal strings on the GPU
+    (csrc/termgen.cu): same arrays, bit for bit."""
+    return _transform(operator, None, 'jw', device)
 
 
-def bravyi_kitaev(operator, n_qubits=None):
+def bravyi_kitaev(operator, n_qubits=None, device=False):
     """Bravyi-Kitaev image (bravyi_kitaev.py:19-52, Fenwick-tree update / parity / occupation
-    sets); n_qubits pads the tree like the reference's argument does."""
-    return _transform(operator, n_qubits, 'bk')
+    sets); n_qubits pads the tree like the reference's argument does; device as above."""
+    return _transform(operator, n_qubits, 'bk', device)
