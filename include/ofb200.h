@@ -53,6 +53,14 @@ int ofb_host_unregister(void *h_ptr);
 int ofb_memcpy_h2d(void *d_dst, const void *h_src, size_t bytes, void *stream);
 int ofb_memcpy_d2h(void *h_dst, const void *d_src, size_t bytes, void *stream);
 int ofb_memcpy_d2d(void *d_dst, const void *d_src, size_t bytes, void *stream);
+/* Blocking copies between device memory and ORDINARY (pageable) host memory through the
+ * library's pinned staging buffers and `threads` worker threads (<= 0: $OFB_COPY_THREADS or half
+ * the cores, at most 8), each on its own stream: the CPU side of the staging -- including the
+ * first touch of freshly allocated destination pages -- runs in parallel and overlaps the DMA.
+ * What numpy.ndarray results of the reference's calls cost to hand over at 2^28 amplitudes or
+ * 7e8 non-zeros (linalg/linear_qubit_operator.py:74-148, linalg/sparse_tools.py:136-194). */
+int ofb_copy_h2d_staged(void *d_dst, const void *h_src, size_t bytes, int device, int threads);
+int ofb_copy_d2h_staged(void *h_dst, const void *d_src, size_t bytes, int device, int threads);
 int ofb_memset(void *d_ptr, int byte, size_t bytes, void *stream);
 int ofb_stream_create(void **stream);
 int ofb_stream_destroy(void *stream);
@@ -343,6 +351,30 @@ int ofb_kws_step(ofb_kws *ws, void *d_w, const void *d_u, const void *d_uprev, v
 int ofb_kws_beta(ofb_kws *ws, int k, void *stream);
 int ofb_kws_fetch(ofb_kws *ws, int count, double *h_alphas, double *h_betas, int *h_flag,
                   void *stream);
+
+/* ---- Davidson's method (csrc/davidson.cu) --------------------------------------------------------
+ * Davidson.get_lowest_n of the reference (linalg/davidson.py:99-221 with _iterate :223-286,
+ * _get_new_directions :288-339, orthonormalize :439-469, append_random_vectors :390-436) as ONE
+ * native call: guess_v / guess_mv are device column blocks, the operator an ofb_linop, the
+ * projected m x m Hermitian problem is solved on the host (ofb_hermitian_eigh), nothing 2^n-long
+ * leaves the device.  d_diag: the operator's real diagonal (dim doubles, device) for the
+ * clamped-inverse preconditioner; d_guess: n_guess start columns (dim complex128 each, contiguous;
+ * n_guess may be 0: seeded random columns); max_subspace / max_iterations / eps / real_only are
+ * DavidsonOptions' fields (linalg/davidson.py:34-68; max_subspace is capped at dim + 1 as
+ * set_dimension does and at what fits in 45 % of the free device memory).  Outputs:
+ * h_eigenvalues[n_lowest] ascending, d_eigenvectors dim x n_lowest column-major (device),
+ * *h_success (max residual norm < eps), *h_iterations, *h_max_error (largest residual norm of the
+ * last iteration), *h_flags bit 0: fewer random vectors than requested could be generated
+ * (the reference's RuntimeWarning). */
+int ofb_davidson_lowest_n(ofb_linop *op, const double *d_diag, int n_lowest, int n_guess,
+                          const void *d_guess, int max_subspace, int max_iterations, double eps,
+                          int real_only, uint64_t seed, double *h_eigenvalues, void *d_eigenvectors,
+                          int *h_success, int *h_iterations, double *h_max_error, int *h_flags,
+                          void *stream);
+/* Eigen-decomposition of a complex Hermitian m x m matrix on the host (numpy.linalg.eigh in
+ * linalg/davidson.py:263): a column-major (re, im) pairs, lower triangle read; w[m] ascending,
+ * z column-major orthonormal eigenvectors.  Householder tridiagonalisation + implicit QL. */
+int ofb_hermitian_eigh(int m, const double *a_ri, double *w, double *z_ri);
 
 #ifdef __cplusplus
 }

@@ -34,6 +34,8 @@ SIGNATURES = {
     'ofb_host_unregister': (c_int, [c_void_p]),
     'ofb_memcpy_h2d': (c_int, [c_void_p, c_void_p, c_size_t, c_void_p]),
     'ofb_memcpy_d2h': (c_int, [c_void_p, c_void_p, c_size_t, c_void_p]),
+    'ofb_copy_h2d_staged': (c_int, [c_void_p, c_void_p, c_size_t, c_int, c_int]),
+    'ofb_copy_d2h_staged': (c_int, [c_void_p, c_void_p, c_size_t, c_int, c_int]),
     'ofb_memcpy_d2d': (c_int, [c_void_p, c_void_p, c_size_t, c_void_p]),
     'ofb_memset': (c_int, [c_void_p, c_int, c_size_t, c_void_p]),
     'ofb_stream_create': (c_int, [P(c_void_p)]),
@@ -121,6 +123,10 @@ SIGNATURES = {
                                    c_uint64, c_int, P(c_double), P(c_double), c_void_p, P(c_int64),
                                    P(c_int), c_void_p]),
     'ofb_tridiag_lowest': (c_int, [c_int, c_void_p, c_void_p, P(c_double), c_void_p]),
+    'ofb_davidson_lowest_n': (c_int, [c_void_p, c_void_p, c_int, c_int, c_void_p, c_int, c_int, c_double,
+                                      c_int, c_uint64, c_void_p, c_void_p, P(c_int), P(c_int),
+                                      P(c_double), P(c_int), c_void_p]),
+    'ofb_hermitian_eigh': (c_int, [c_int, c_void_p, c_void_p, c_void_p]),
     'ofb_kws_create': (c_int, [c_int64, c_int, c_int, P(c_void_p)]),
     'ofb_kws_destroy': (c_int, [c_void_p]),
     'ofb_kws_scalars': (c_int, [c_void_p, P(c_void_p)]),
@@ -237,7 +243,7 @@ def to_host(buf, shape, dtype, byte_offset=0, stream=None):
     return out
 
 
-def parallel_d2h(pairs, device=0, threads=None, chunk=1 << 27):
+def parallel_d2h(pairs, device=0, threads=None, chunk=1 << 27, pretouch=None, staged=None):
     """Device -> host copies of large results into ordinary (pageable, usually untouched) numpy
     arrays from several host threads, each on its own stream.  `pairs` = [(host array, device
     pointer)].  A pageable copy stages through the driver's pinned buffer and the CPU copy out of
@@ -245,7 +251,11 @@ def parallel_d2h(pairs, device=0, threads=None, chunk=1 << 27):
     in the calling thread; ctypes releases the GIL, so the threads overlap.  Measured on the
     B200 box (16 cores): 4 GB into fresh memory 0.85 s from one thread."""
     import concurrent.futures
-    threads = threads or max(1, min(8, (os.cpu_count() or 2) // 2))
+    threads = threads or int(os.environ.get('OFB_D2H_THREADS', '0')) or max(1, min(8, (os.cpu_count() or 2) // 2))
+    if pretouch is None:
+        pretouch = os.environ.get('OFB_D2H_PRETOUCH', '1') == '1'
+    if staged is None:
+        staged = os.environ.get('OFB_STAGED_COPY', '1') != '0'
     jobs = []
     for host, dev_ptr in pairs:
         base, nbytes = host.ctypes.data, host.nbytes
@@ -256,6 +266,11 @@ def parallel_d2h(pairs, device=0, threads=None, chunk=1 << 27):
                                           c_int(14))  # MADV_HUGEPAGE
         except Exception:
             pass
+        if staged:
+            # the library's own pinned staging + worker threads (csrc/hostcopy.cu)
+            call('ofb_copy_d2h_staged', c_void_p(base), c_void_p(dev_ptr), c_size_t(nbytes), c_int(device),
+                 c_int(threads))
+            continue
         for off in range(0, nbytes, chunk):
             jobs.append((base + off, dev_ptr + off, min(chunk, nbytes - off)))
     if not jobs:
@@ -268,6 +283,11 @@ def parallel_d2h(pairs, device=0, threads=None, chunk=1 << 27):
         call('ofb_stream_create', ctypes.byref(stream))
         try:
             for dst, src, size in jobs[k::threads]:
+                # first touch outside the copy: a plain memset faults fresh pages several times
+                # faster than the driver's pageable path does (4 GB: 0.85 s into fresh memory,
+                # 0.25 s into touched memory), and memsets of different threads run in parallel
+                if pretouch:
+                    ctypes.memset(c_void_p(dst), 0, size)
                 call('ofb_memcpy_d2h', c_void_p(dst), c_void_p(src), c_size_t(size), stream)
             call('ofb_stream_sync', stream)
         finally:

@@ -24,7 +24,6 @@
 // (the per-term work is shared by twice as many amplitudes) at 12 instead of 16 warps per SM.
 #include <algorithm>
 #include <cstdlib>
-#include <thread>
 
 #include "ofb_internal.cuh"
 
@@ -683,41 +682,20 @@ int launch_apply_multi(ofb_plan *p, const void *d_in, void *d_out, int ncols, in
 // With the orbit-reduced tables the shared per-term work is under a third of the instructions,
 // and in the single-column kernel it doubles as latency hiding for the 16 gathers it follows; the
 // batched kernel's second phase has nothing to overlap its gathers with at 8 warps per SM.
-// Host -> device copy of a caller's (pageable) vector.  A pageable copy stages through the driver's
-// pinned buffer and the CPU side of that staging runs in the calling thread (measured: 4 GB in
-// 0.39 s = 11 GB/s from one thread); large vectors are therefore cut into pieces copied from
-// several host threads so that staging and DMA of different pieces overlap.
+// Host -> device copy of a caller's (pageable) vector: above 64 MB through the library's own
+// pinned staging and worker threads (hostcopy.cu; a plain pageable cudaMemcpy runs at 11 GB/s and
+// the driver serialises several of them), OFB_STAGED_COPY=0 keeps the plain copy.
+static inline bool staged_ok(size_t bytes) {
+    const char *env = getenv("OFB_STAGED_COPY");
+    return bytes >= ((size_t)64 << 20) && !(env && env[0] == '0');
+}
 static int host_to_device(void *d_dst, const void *h_src, size_t bytes, int device, cudaStream_t s) {
-    const size_t piece_min = (size_t)128 << 20;
-    const char *env = getenv("OFB_H2D_THREADS");
-    int threads = env ? atoi(env) : 4;
-    threads = (int)std::min<size_t>((size_t)std::max(threads, 1), bytes / piece_min);
-    if (threads <= 1) {
+    if (!staged_ok(bytes)) {
         OFB_CUDA(cudaMemcpyAsync(d_dst, h_src, bytes, cudaMemcpyHostToDevice, s));
         return OFB_OK;
     }
-    OFB_CUDA(cudaStreamSynchronize(s));  // the pieces go out on per-thread streams
-    std::vector<std::thread> pool;
-    std::vector<cudaError_t> status((size_t)threads, cudaSuccess);
-    const size_t piece = ((bytes / threads) + 255) & ~(size_t)255;
-    for (int t = 0; t < threads; ++t) {
-        pool.emplace_back([=, &status]() {
-            const size_t lo = (size_t)t * piece, hi = std::min(bytes, lo + piece);
-            if (lo >= hi) return;
-            cudaError_t e = cudaSetDevice(device);
-            cudaStream_t ts = nullptr;
-            if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&ts, cudaStreamNonBlocking);
-            if (e == cudaSuccess)
-                e = cudaMemcpyAsync((char *)d_dst + lo, (const char *)h_src + lo, hi - lo, cudaMemcpyHostToDevice, ts);
-            if (e == cudaSuccess) e = cudaStreamSynchronize(ts);
-            if (ts) cudaStreamDestroy(ts);
-            status[(size_t)t] = e;
-        });
-    }
-    for (auto &th : pool) th.join();
-    for (cudaError_t e : status)
-        if (e != cudaSuccess) return cuda_fail(e, "threaded host-to-device copy", __FILE__, __LINE__);
-    return OFB_OK;
+    OFB_CUDA(cudaStreamSynchronize(s));  // the pieces go out on the workers' streams
+    return staged_copy(d_dst, const_cast<void *>(h_src), bytes, true, device, 0);
 }
 
 static inline bool multi_ok(const ofb_plan *p, int ncols) {
@@ -850,8 +828,14 @@ int ofb_apply_host(ofb_plan *p, const void *h_in, void *h_out, int ncols) {
         if (slabs == 1) {
             rc = launch_apply(p, p->d_stage_in, p->d_stage_out, p->n_qubits, 0, 0, p->n_groups, 0, s);
             if (rc) return rc;
-            OFB_CUDA(cudaMemcpyAsync((char *)h_out + c * col_bytes, p->d_stage_out, col_bytes,
-                                     cudaMemcpyDeviceToHost, s));
+            if (staged_ok(col_bytes)) {
+                OFB_CUDA(cudaStreamSynchronize(s));
+                if ((rc = staged_copy(p->d_stage_out, (char *)h_out + c * col_bytes, col_bytes, false, p->device, 0)))
+                    return rc;
+            } else {
+                OFB_CUDA(cudaMemcpyAsync((char *)h_out + c * col_bytes, p->d_stage_out, col_bytes,
+                                         cudaMemcpyDeviceToHost, s));
+            }
             continue;
         }
         const uint64_t per = tiles / slabs;
@@ -862,10 +846,15 @@ int ofb_apply_host(ofb_plan *p, const void *h_in, void *h_out, int ncols) {
         }
         const size_t slab_bytes = col_bytes / slabs;
         for (int k = 0; k < slabs; ++k) {
-            OFB_CUDA(cudaStreamWaitEvent(p->copy_stream, p->slab_done[k], 0));
-            OFB_CUDA(cudaMemcpyAsync((char *)h_out + c * col_bytes + k * slab_bytes,
-                                     (const char *)p->d_stage_out + k * slab_bytes, slab_bytes,
-                                     cudaMemcpyDeviceToHost, p->copy_stream));
+            char *dst = (char *)h_out + c * col_bytes + k * slab_bytes;
+            const char *src = (const char *)p->d_stage_out + k * slab_bytes;
+            if (staged_ok(slab_bytes)) {  // worker threads fault the caller's pages in parallel
+                OFB_CUDA(cudaEventSynchronize(p->slab_done[k]));
+                if ((rc = staged_copy(const_cast<char *>(src), dst, slab_bytes, false, p->device, 0))) return rc;
+            } else {
+                OFB_CUDA(cudaStreamWaitEvent(p->copy_stream, p->slab_done[k], 0));
+                OFB_CUDA(cudaMemcpyAsync(dst, src, slab_bytes, cudaMemcpyDeviceToHost, p->copy_stream));
+            }
         }
         OFB_CUDA(cudaStreamSynchronize(p->copy_stream));  // stage_out is free for the next column
     }

@@ -29,6 +29,10 @@ constexpr int TB = 64;                 // threads per CTA (== 1 << CLASS_SHIFT)
 constexpr int TR = 1 << CLASS_BITS;    // columns per thread
 constexpr int TTILE = TB * TR;
 constexpr int TTILE_BITS = CLASS_SHIFT + CLASS_BITS;
+#ifndef OFB_CSC_QW
+#define OFB_CSC_QW 4
+#endif
+constexpr int QW = OFB_CSC_QW;  // columns whose position lookups are in flight together
 static_assert(CLASS_BITS == 4 && CLASS_SHIFT == 6, "csc_tile.cu assumes the 64 x 16 geometry");
 
 struct CscStage {
@@ -115,20 +119,26 @@ __device__ __noinline__ double2 csc_group_rows(const ScatterRow *__restrict__ ro
     return make_double2(sr, si);
 }
 
+// blockIdx.x = tile * n_slices + slice: a tile of 1 024 columns and a slice of the group list
+// (whole groups in x order; see csc_slice_count).  The slices of a tile are neighbours in launch
+// order, so the tiles being written at any time are few.
+// slice = (first chunk, end chunk, first segment, end segment).
 template <bool FILL, bool HAS_IMAG, typename I>
 __global__ void __launch_bounds__(TB, 6)
-k_csc_tile(const Chunk *__restrict__ chunks, uint32_t n_chunks, const Segment *__restrict__ segs,
+k_csc_tile(const Chunk *__restrict__ chunks, const uint4 *__restrict__ slices, uint32_t n_slices,
+           const Segment *__restrict__ segs,
            const uint32_t *__restrict__ seg_group, const TermZC *__restrict__ zc_re,
            const TermZC *__restrict__ zc_im, const uint32_t *__restrict__ sib,
            const uint8_t *__restrict__ group_slow, const ScatterRow *__restrict__ rows,
            const GroupDesc *__restrict__ groups, int n, uint64_t dim, uint32_t words,
-           uint32_t *__restrict__ bitmap, uint32_t *__restrict__ prefix, int64_t *__restrict__ colcount,
+           uint32_t *__restrict__ bitmap, const uint32_t *__restrict__ prefix,
            const int64_t *__restrict__ colptr, I *__restrict__ indices, double2 *__restrict__ data) {
     __shared__ CscStage sbuf[2];
     __shared__ uint32_t s_sib[2][CHUNK_MAX_SEGS][32];
     __shared__ uint32_t s_group[2][CHUNK_MAX_SEGS];
     const uint32_t tid = threadIdx.x, lane = tid & 31;
-    const uint32_t c0 = blockIdx.x * (uint32_t)TTILE + tid;  // column of r = 0
+    const uint32_t tile = blockIdx.x / n_slices;
+    const uint32_t c0 = tile * (uint32_t)TTILE + tid;  // column of r = 0
 
     double vr[TR], vi[TR];
 #pragma unroll
@@ -142,16 +152,19 @@ k_csc_tile(const Chunk *__restrict__ chunks, uint32_t n_chunks, const Segment *_
         }
     };
 
-    Chunk cur = chunks[0];
-    Chunk nxt = n_chunks > 1 ? chunks[1] : cur;
+    const uint4 slice = slices[blockIdx.x - tile * n_slices];
+    const uint32_t ch0 = slice.x, ch1 = slice.y, seg0 = slice.z, seg1 = slice.w;
+    Chunk cur = chunks[ch0];
+    Chunk nxt = ch0 + 1 < ch1 ? chunks[ch0 + 1] : cur;
     csc_stage(sbuf[0], cur, segs, zc_re, zc_im, HAS_IMAG);
     stage_aux(0, cur);
-    for (uint32_t c = 0; c < n_chunks; ++c) {
+    for (uint32_t cc = ch0; cc < ch1; ++cc) {
+        const uint32_t c = cc - ch0;  // buffer parity
         Chunk after = nxt;
-        if (c + 1 < n_chunks) {
+        if (cc + 1 < ch1) {
             csc_stage(sbuf[(c + 1) & 1], nxt, segs, zc_re, zc_im, HAS_IMAG);
             stage_aux((c + 1) & 1, nxt);
-            if (c + 2 < n_chunks) after = chunks[c + 2];
+            if (cc + 2 < ch1) after = chunks[cc + 2];
             asm volatile("cp.async.wait_group 1;\n" ::: "memory");
         } else {
             asm volatile("cp.async.wait_group 0;\n" ::: "memory");
@@ -159,6 +172,7 @@ k_csc_tile(const Chunk *__restrict__ chunks, uint32_t n_chunks, const Segment *_
         __syncthreads();
         const CscStage &b = sbuf[c & 1];
         for (uint32_t q = 0; q < cur.seg_count; ++q) {
+            if (cur.seg_begin + q < seg0 || cur.seg_begin + q >= seg1) continue;  // another slice's groups
             const Segment &sd = b.segs[q];
             const uint32_t g = s_group[c & 1][q];
             const uint32_t runs = sd.kind_runs & 0xfu, kind = sd.kind_runs >> 30;
@@ -208,24 +222,44 @@ k_csc_tile(const Chunk *__restrict__ chunks, uint32_t n_chunks, const Segment *_
                 base += set ? sv : 0u;
                 delta[k] = set ? -(int32_t)sv : (int32_t)sv;  // toggling bit k of r toggles that row bit
             }
+            // Four columns at a time: the position lookups (bitmap word, prefix count, column start)
+            // of all four are issued before the first store, so their latencies overlap -- with one
+            // column at a time the pass was bound by 12 warps per SM each waiting on one load chain
+            // (ncu: 33 warp-cycles of long-scoreboard stall per issued instruction).
 #pragma unroll
-            for (int r = 0; r < TR; ++r) {
-                const double re = vr[r], im = vi[r];
-                vr[r] = 0.0;
-                vi[r] = 0.0;
-                if (re == 0.0 && im == 0.0) continue;
-                int32_t rank = (int32_t)base;
+            for (int r0 = 0; r0 < TR; r0 += QW) {
+                bool nz[QW];
+                int32_t rank[QW];
+                uint32_t bm[QW], pf[QW];
+                int64_t cp[QW];
 #pragma unroll
-                for (int k = 0; k < CLASS_BITS; ++k) rank += ((r >> k) & 1) ? delta[k] : 0;
-                const uint64_t col = (uint64_t)(c0 + r * TB);
-                const size_t at = (size_t)((uint32_t)rank >> 5) * dim + col;
-                if (!FILL) {
-                    bitmap[at] |= 1u << (rank & 31);
-                } else {
-                    const uint32_t below = bitmap[at] & ((1u << (rank & 31)) - 1u);
-                    const int64_t pos = colptr[col] + prefix[at] + __popc(below);
-                    indices[pos] = (I)(col ^ (uint64_t)x);
-                    data[pos] = make_double2(re, im);
+                for (int q = 0; q < QW; ++q) {
+                    const int r = r0 + q;
+                    nz[q] = !(vr[r] == 0.0 && vi[r] == 0.0);
+                    rank[q] = (int32_t)base;
+#pragma unroll
+                    for (int k = 0; k < CLASS_BITS; ++k) rank[q] += ((r >> k) & 1) ? delta[k] : 0;
+                    const uint64_t col = (uint64_t)(c0 + r * TB);
+                    const size_t at = (size_t)((uint32_t)rank[q] >> 5) * dim + col;
+                    if (!FILL) {
+                        if (nz[q]) atomicOr(&bitmap[at], 1u << (rank[q] & 31));  // other slices set other bits
+                    } else {
+                        bm[q] = nz[q] ? bitmap[at] : 0u;
+                        pf[q] = nz[q] ? prefix[at] : 0u;
+                        cp[q] = nz[q] ? colptr[col] : 0;
+                    }
+                }
+#pragma unroll
+                for (int q = 0; q < QW; ++q) {
+                    const int r = r0 + q;
+                    if (FILL && nz[q]) {
+                        const uint64_t col = (uint64_t)(c0 + r * TB);
+                        const int64_t pos = cp[q] + pf[q] + __popc(bm[q] & ((1u << (rank[q] & 31)) - 1u));
+                        indices[pos] = (I)(col ^ (uint64_t)x);
+                        data[pos] = make_double2(vr[r], vi[r]);
+                    }
+                    vr[r] = 0.0;
+                    vi[r] = 0.0;
                 }
             }
         }
@@ -233,18 +267,21 @@ k_csc_tile(const Chunk *__restrict__ chunks, uint32_t n_chunks, const Segment *_
         cur = nxt;
         nxt = after;
     }
-    if (!FILL) {
-#pragma unroll 1
-        for (int r = 0; r < TR; ++r) {
-            const uint64_t col = (uint64_t)(c0 + r * TB);
-            uint32_t run = 0;
-            for (uint32_t w = 0; w < words; ++w) {
-                prefix[(size_t)w * dim + col] = run;
-                run += __popc(bitmap[(size_t)w * dim + col]);
-            }
-            colcount[col] = run;
-        }
+}
+
+// per-column prefix counts of the rank bitmap (after ALL slices of the count pass): prefix[w][c] =
+// non-zeros of column c in words < w, colcount[c] = their total.  One thread per column, coalesced.
+__global__ void __launch_bounds__(256)
+k_csc_prefix(uint64_t dim, uint32_t words, const uint32_t *__restrict__ bitmap, uint32_t *__restrict__ prefix,
+             int64_t *__restrict__ colcount) {
+    const uint64_t col = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (col >= dim) return;
+    uint32_t run = 0;
+    for (uint32_t w = 0; w < words; ++w) {
+        prefix[(size_t)w * dim + col] = run;
+        run += __popc(bitmap[(size_t)w * dim + col]);
     }
+    colcount[col] = run;
 }
 
 // host side: per-segment group ids / last flags and the slow-group table, built on first use
@@ -267,6 +304,68 @@ int csc_tile_prepare(ofb_plan *p) {
     OFB_CATCH((void)0)
 }
 
+// Slices of the group list (whole groups in x order, balanced by terms + a per-group constant for
+// the rank and store work), one CTA per (tile, slice).  Two reasons to cut:
+// (1) a small matrix has too few column tiles to fill 148 SMs x 6 CTAs;
+// (2) the fill pass appends 16 + 4 bytes per entry to 1 024 columns whose output ranges lie
+//     kilobytes apart, so every 32-byte sector is written in 2 (data) or 8 (indices) separate
+//     stores and is complete only if it stays in L2 until the last of them.  With one CTA per
+//     tile the 888 resident CTAs have their whole output open at once (14.9 GB at config 2): ncu
+//     showed 39 GB written + 35 GB read for those 14.9 GB -- sectors evicted half written and
+//     read back.  With S slices per tile only 888 / S tiles are open; measured on B200 the pass
+//     is fastest when the open output is ~17 MB (config 2: S = 768, 54.9 -> 17.0 ms; 24-qubit
+//     Hubbard: S = 24, 25.9 -> 7.1 ms).  Visiting the groups in ROW order instead (blocks of
+//     equal high x bits sorted by key ^ c_hi per tile, so that each column advances monotonically)
+//     was built and measured: no gain at S = 1 (51.5 ms: an index sector still waits for 8
+//     entries of its column while the chip writes 165 MB) and slower than x-order slices at equal
+//     S, so it was dropped (profiles/README.md).
+// OFB_CSC_COUNT_SLICES / OFB_CSC_FILL_SLICES / OFB_CSC_SLICES override the choice.
+static uint32_t csc_slice_count(const ofb_plan *p, bool fill, double bytes_per_tile) {
+    const char *env = getenv(fill ? "OFB_CSC_FILL_SLICES" : "OFB_CSC_COUNT_SLICES");
+    if (!env) env = getenv("OFB_CSC_SLICES");
+    const uint32_t G = (uint32_t)p->n_groups;
+    if (env) return std::min<uint32_t>(std::max(atoi(env), 1), G);
+    const double tiles = (double)((1ull << p->n_qubits) / TTILE);
+    const double resident = 148.0 * 6.0;
+    double s = std::ceil(4.0 * resident / tiles);  // (1) at least ~4 waves of CTAs
+    if (fill && bytes_per_tile > 0.0) s = std::max(s, std::ceil(resident * bytes_per_tile / 17e6));  // (2)
+    s = std::min(s, std::floor((double)G / 3.0));  // a slice keeps >= 3 groups: staging + prologue per CTA
+    return (uint32_t)std::min<double>(std::max(s, 1.0), 4096.0);
+}
+
+static int csc_tile_slices(ofb_plan *p, uint32_t want, uint4 **d_out, uint32_t *n_out) {
+    OFB_TRY
+    const uint32_t G = (uint32_t)p->n_groups;
+    want = std::min(std::max(want, 1u), G);
+    if (*d_out && *n_out == want) return OFB_OK;
+    // weight of a group: its terms + 16 (rank computation and up to 16 stores per thread)
+    std::vector<double> acc(G + 1, 0.0);
+    for (uint32_t g = 0; g < G; ++g)
+        acc[g + 1] = acc[g] + (double)(p->h_group_begin[g + 1] - p->h_group_begin[g]) + 16.0;
+    std::vector<uint4> slices;
+    uint32_t g0 = 0;
+    for (uint32_t k = 1; k <= want; ++k) {
+        // slice k ends at the first group boundary at or after its share of the weight, but
+        // leaves at least one group for every slice still to come
+        uint32_t g1 = G;
+        if (k < want) {
+            const double target = acc[G] * k / want;
+            g1 = (uint32_t)(std::lower_bound(acc.begin(), acc.end(), target) - acc.begin());
+            g1 = std::min(std::max(g1, g0 + 1), G - (want - k));
+        }
+        const uint32_t seg0 = p->h_seg_begin[g0], seg1 = p->h_seg_begin[g1];
+        slices.push_back(make_uint4(p->h_chunk_of_seg[seg0], p->h_chunk_of_seg[seg1 - 1] + 1, seg0, seg1));
+        g0 = g1;
+    }
+    cudaFree(*d_out);
+    *d_out = nullptr;
+    OFB_CUDA(cudaMalloc(d_out, slices.size() * sizeof(uint4)));
+    OFB_CUDA(cudaMemcpy(*d_out, slices.data(), slices.size() * sizeof(uint4), cudaMemcpyHostToDevice));
+    *n_out = (uint32_t)slices.size();
+    return OFB_OK;
+    OFB_CATCH((void)0)
+}
+
 bool csc_tile_ok(const ofb_plan *p) {
     return !p->projected && p->n_qubits >= TTILE_BITS && p->n_qubits <= 30 && p->n_groups > 0 &&
            p->d_segs != nullptr;
@@ -275,17 +374,21 @@ bool csc_tile_ok(const ofb_plan *p) {
 int csc_tile_count(ofb_plan *p, uint32_t words, uint32_t *bitmap, uint32_t *prefix, int64_t *counts,
                    cudaStream_t s) {
     int rc = csc_tile_prepare(p);
+    if (!rc) rc = csc_tile_slices(p, csc_slice_count(p, false, 0.0), &p->d_count_slices, &p->n_count_slices);
     if (rc) return rc;
     const uint64_t dim = 1ull << p->n_qubits;
     OFB_CUDA(cudaMemsetAsync(bitmap, 0, (size_t)words * dim * sizeof(uint32_t), s));
-    const unsigned grid = (unsigned)(dim / TTILE);
+    const uint32_t n_slices = p->n_count_slices;
+    const unsigned grid = (unsigned)(dim / TTILE) * n_slices;
 #define OFB_TILE(II)                                                                              \
     k_csc_tile<false, II, int32_t><<<grid, TB, 0, s>>>(                                           \
-        p->d_chunks, (uint32_t)p->n_chunks, p->d_segs, p->d_seg_group, p->d_zc, p->d_zc_im, p->d_sib, \
-        p->d_group_slow, p->d_rows, p->d_groups, p->n_qubits, dim, words, bitmap, prefix, counts,  \
-        nullptr, (int32_t *)nullptr, nullptr)
+        p->d_chunks, p->d_count_slices, n_slices, p->d_segs, p->d_seg_group, p->d_zc, p->d_zc_im, p->d_sib,       \
+        p->d_group_slow, p->d_rows, p->d_groups, p->n_qubits, dim, words, bitmap, prefix, nullptr, \
+        (int32_t *)nullptr, nullptr)
     if (p->has_imag) OFB_TILE(true); else OFB_TILE(false);
 #undef OFB_TILE
+    OFB_LAUNCH_CHECK();
+    k_csc_prefix<<<(unsigned)((dim + 255) / 256), 256, 0, s>>>(dim, words, bitmap, prefix, counts);
     OFB_LAUNCH_CHECK();
     return OFB_OK;
 }
@@ -293,11 +396,15 @@ int csc_tile_count(ofb_plan *p, uint32_t words, uint32_t *bitmap, uint32_t *pref
 int csc_tile_fill(ofb_plan *p, uint32_t words, uint32_t *bitmap, uint32_t *prefix, const int64_t *colptr,
                   void *d_indices, void *d_data, int index_bits, cudaStream_t s) {
     const uint64_t dim = 1ull << p->n_qubits;
-    const unsigned grid = (unsigned)(dim / TTILE);
+    const double bytes_per_tile = (double)p->csc_nnz * (16.0 + index_bits / 8) / (double)(dim / TTILE);
+    int rc = csc_tile_slices(p, csc_slice_count(p, true, bytes_per_tile), &p->d_fill_slices, &p->n_fill_slices);
+    if (rc) return rc;
+    const uint32_t n_slices = p->n_fill_slices;
+    const unsigned grid = (unsigned)(dim / TTILE) * n_slices;
 #define OFB_TILE(II, TT)                                                                          \
     k_csc_tile<true, II, TT><<<grid, TB, 0, s>>>(                                                 \
-        p->d_chunks, (uint32_t)p->n_chunks, p->d_segs, p->d_seg_group, p->d_zc, p->d_zc_im, p->d_sib, \
-        p->d_group_slow, p->d_rows, p->d_groups, p->n_qubits, dim, words, bitmap, prefix, nullptr, \
+        p->d_chunks, p->d_fill_slices, n_slices, p->d_segs, p->d_seg_group, p->d_zc, p->d_zc_im, p->d_sib,       \
+        p->d_group_slow, p->d_rows, p->d_groups, p->n_qubits, dim, words, bitmap, prefix,         \
         colptr, (TT *)d_indices, (double2 *)d_data)
     if (index_bits == 32) {
         if (p->has_imag) OFB_TILE(true, int32_t); else OFB_TILE(false, int32_t);

@@ -220,6 +220,10 @@ struct ofb_plan {
     uint32_t *d_seg_group = nullptr;
     uint8_t *d_group_slow = nullptr;
     std::vector<uint8_t> h_group_slow;
+    // slices of the group list for the tiled CSC passes: (first chunk, end chunk, first segment,
+    // end segment) per slice; the count and fill passes choose their own number
+    uint4 *d_count_slices = nullptr, *d_fill_slices = nullptr;
+    uint32_t n_count_slices = 0, n_fill_slices = 0;
     // CSC state between count and fill
     int64_t *d_colptr = nullptr;   // 2^n + 1 exclusive scan of counts
     uint32_t *d_bitmap = nullptr;  // [words][2^n] rank-ordered non-zero flags
@@ -254,6 +258,9 @@ int csc_exact_count(ofb_plan *plan, int64_t *d_counts, cudaStream_t s);
 int csc_exact_fill(ofb_plan *plan, const int64_t *d_colptr, void *d_indices, void *d_data,
                    int index_bits, cudaStream_t s);
 // csc_tile.cu: tiled count / fill passes for Pauli plans (term tables shared by 1 024 columns)
+// hostcopy.cu: blocking copy between a device pointer and pageable host memory through pinned
+// staging buffers and worker threads (threads <= 0: OFB_COPY_THREADS or half the cores, at most 8)
+int staged_copy(void *d, void *h, size_t bytes, bool to_device, int device, int threads);
 bool csc_tile_ok(const ofb_plan *plan);
 int csc_tile_count(ofb_plan *plan, uint32_t words, uint32_t *bitmap, uint32_t *prefix, int64_t *counts,
                    cudaStream_t s);

@@ -499,6 +499,8 @@ int ofb_plan_destroy(ofb_plan *p) {
     cudaFree(p->d_sib);
     cudaFree(p->d_seg_group);
     cudaFree(p->d_group_slow);
+    cudaFree(p->d_count_slices);
+    cudaFree(p->d_fill_slices);
     cudaFree(p->d_colptr);
     cudaFree(p->d_bitmap);
     cudaFree(p->d_partials);

@@ -14,6 +14,7 @@ reference's trajectory-pinning tests (davidson_test.py:205-311) hold.  What move
     reference's modified Gram-Schmidt).
 """
 import logging
+import os
 import warnings
 
 import numpy
@@ -213,6 +214,13 @@ class Davidson:
 
         op = self._prepare_device()
         eps = self.options.eps
+        if (hasattr(op, 'linop') and os.environ.get('OFB_DAVIDSON_HOST') != '1'
+                and not logging.getLogger().isEnabledFor(logging.INFO)):
+            # the whole loop behind the C ABI (csrc/davidson.cu); the host-driven loop below stays
+            # for operators whose matvec is host code and for callers who want the reference's
+            # per-iteration log line (logging at INFO)
+            return self._get_lowest_n_native(op, n_lowest, initial_guess,
+                                             max_iterations or self.options.max_iterations)
         capacity = max(self._capacity(dim, n_lowest), initial_guess.shape[1] + n_lowest)
         max_subspace = min(self.options.max_subspace, capacity - n_lowest)
         V = _ColumnBlock(dim, capacity)
@@ -284,6 +292,44 @@ class Davidson:
             for block in (V, MV, TV, TMV):
                 block.free()
             R.free()
+
+    def _get_lowest_n_native(self, op, n_lowest, initial_guess, max_iterations):
+        """ofb_davidson_lowest_n (include/ofb200.h): same iteration, no Python in the loop."""
+        dim = len(self.linear_operator_diagonal)
+        guess = _ColumnBlock(dim, initial_guess.shape[1])
+        out = _ColumnBlock(dim, n_lowest)
+        values = numpy.zeros(n_lowest)
+        success, iterations, flags = _lib.c_int(), _lib.c_int(), _lib.c_int()
+        error = c_double()
+        handle = op.linop()
+        try:
+            guess.upload(initial_guess)
+            seed = int(numpy.random.randint(0, 2**31 - 1))  # numpy's seed governs random restarts
+            _lib.call('ofb_davidson_lowest_n', handle, c_void_p(self._d_diag.ptr), _lib.c_int(n_lowest),
+                      _lib.c_int(guess.count), c_void_p(guess.col(0)), _lib.c_int(self.options.max_subspace),
+                      _lib.c_int(max_iterations), c_double(self.options.eps),
+                      _lib.c_int(1 if self.options.real_only else 0), _lib.ctypes.c_uint64(seed),
+                      _lib.ptr(values), c_void_p(out.col(0)), _lib.ctypes.byref(success),
+                      _lib.ctypes.byref(iterations), _lib.ctypes.byref(error), _lib.ctypes.byref(flags),
+                      c_void_p(None))
+            out.count = n_lowest
+            eigen_vectors = out.download()
+        finally:
+            _lib.call('ofb_linop_destroy', handle)
+            guess.free()
+            out.free()
+        self.last_iterations = iterations.value
+        self.last_error = error.value
+        if flags.value & 1:
+            warnings.warn('Unable to generate specified number of random vectors: '
+                          'the search space could not be extended.', RuntimeWarning)
+        if self.options.real_only and not numpy.allclose(numpy.real(eigen_vectors), eigen_vectors):
+            warnings.warn(
+                'Unable to get real only eigenvectors, return '
+                'complex vectors instead with success state {}.'.format(bool(success.value)),
+                RuntimeWarning,
+            )
+        return bool(success.value), values, numpy.ascontiguousarray(eigen_vectors)
 
     @staticmethod
     def _max_imag(dim, column_ptr):

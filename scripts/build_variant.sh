@@ -3,10 +3,8 @@
 set -e
 name=$1; shift
 mkdir -p variants/$name
-for f in plan apply vec csc csc_exact sector; do
+for f in $(cd openfermion_b200/csrc && ls *.cu | sed 's/\.cu$//'); do
   nvcc -gencode arch=compute_100a,code=sm_100a -lineinfo -O3 -std=c++17 -Xcompiler -fPIC -Xcompiler -fvisibility=default "$@" -Xptxas -v -I include -c openfermion_b200/csrc/$f.cu -o variants/$name/$f.o 2> variants/$name/$f.log &
 done
 wait
 nvcc -gencode arch=compute_100a,code=sm_100a -shared -o variants/libofb200_$name.so variants/$name/*.o -lcudart
-grep -A1 "k_apply8ILb1ELb0ELb0" variants/$name/apply.log | grep -E "registers|spill" | head -3
-grep "Used" variants/$name/apply.log | sed -n 2p

@@ -44,7 +44,31 @@ def run(name, op, n, mode):
     plan.close()
 
 
+def sweep(which):
+    """slice counts of the tiled passes (OFB_CSC_COUNT_SLICES / OFB_CSC_FILL_SLICES)"""
+    cases = {'mol20': ('molecular dyadic', lambda: hamiltonians.molecular_jw(10, seed=1234, dyadic_bits=16), 20),
+             'hub24': ('hubbard 3x4', lambda: hamiltonians.hubbard_jw(3, 4), 24),
+             'mol16': ('molecular', lambda: hamiltonians.molecular_jw(8, seed=1234), 16)}
+    name, make, n = cases[which]
+    op = make()
+    for s in [int(t) for t in os.environ.get('CSC_SWEEP_LIST', '0,1,2,4,8,16,32,64,128,256').split(',')]:
+        for key in ('OFB_CSC_COUNT_SLICES', 'OFB_CSC_FILL_SLICES'):
+            if s:
+                os.environ[key] = str(s)
+            else:
+                os.environ.pop(key, None)
+        for _ in range(2):
+            run('%s slices=%s' % (name, s or 'auto'), op, n, 0)
+
+
 if __name__ == '__main__':
+    if len(sys.argv) > 2 and sys.argv[1] == '--sweep':
+        sweep(sys.argv[2])
+        sys.exit(0)
+    if len(sys.argv) > 2 and sys.argv[1] == '--one':  # a single build, for ncu
+        sweep.__globals__['run'](*{'mol20': ('molecular dyadic', hamiltonians.molecular_jw(10, seed=1234, dyadic_bits=16), 20, 0),
+                                   'hub24': ('hubbard 3x4', hamiltonians.hubbard_jw(3, 4), 24, 0)}[sys.argv[2]])
+        sys.exit(0)
     run('molecular dyadic', hamiltonians.molecular_jw(10, seed=1234, dyadic_bits=16), 20, 0)
     run('molecular', hamiltonians.molecular_jw(7, seed=1234), 14, 1)
     run('molecular', hamiltonians.molecular_jw(7, seed=1234), 14, 0)

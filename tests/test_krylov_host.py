@@ -4,6 +4,7 @@ used: scipy.linalg.eigh_tridiagonal(select='i'))."""
 import ctypes
 
 import numpy
+import pytest
 import scipy.linalg
 
 from openfermion_b200 import _lib
@@ -59,3 +60,44 @@ def test_tridiag_lowest_lanczos_like_matrix_with_ghost_copies():
     value, vector = _lowest(numpy.array(alphas), numpy.array(betas[:-1]))
     assert abs(value - spectrum[0]) < 1e-12
     assert abs(betas[-1] * vector[-1]) < 1e-8
+
+
+# ---- ofb_hermitian_eigh: the projected problem of the native Davidson loop (csrc/davidson.cu) -----
+def _eigh(a):
+    m = a.shape[0]
+    lower = numpy.asfortranarray(numpy.tril(a))  # only the lower triangle is read
+    w = numpy.zeros(m)
+    z = numpy.zeros((m, m), dtype=numpy.complex128, order='F')
+    _lib.call('ofb_hermitian_eigh', ctypes.c_int(m), _lib.ptr(lower), _lib.ptr(w), _lib.ptr(z))
+    return w, z
+
+
+def test_hermitian_eigh_matches_lapack():
+    rng = numpy.random.default_rng(7)
+    for m in (1, 2, 3, 5, 17, 64, 101):
+        for kind in ('complex', 'diagonal', 'degenerate', 'real', 'graded'):
+            a = rng.normal(size=(m, m)) + 1j * rng.normal(size=(m, m))
+            a = a + a.conj().T
+            if kind == 'diagonal':
+                a = numpy.diag(rng.normal(size=m)).astype(complex)
+            elif kind == 'degenerate':
+                q, _ = numpy.linalg.qr(a)
+                a = q @ numpy.diag(numpy.repeat(rng.normal(size=(m + 2) // 3), 3)[:m]) @ q.conj().T
+                a = (a + a.conj().T) / 2
+            elif kind == 'real':
+                a = a.real.astype(complex)
+            elif kind == 'graded':
+                s = numpy.diag(10.0 ** -numpy.linspace(0, 8, m))
+                a = s @ a @ s
+            w, z = _eigh(a)
+            scale = max(1.0, numpy.max(numpy.abs(a)))
+            assert numpy.all(numpy.diff(w) >= 0)
+            assert numpy.max(numpy.abs(w - numpy.linalg.eigvalsh(a))) < 1e-12 * scale * m
+            assert numpy.max(numpy.abs(a @ z - z * w)) < 1e-12 * scale * m
+            assert numpy.max(numpy.abs(z.conj().T @ z - numpy.eye(m))) < 1e-12 * m
+
+
+def test_hermitian_eigh_argument_checks():
+    with pytest.raises(_lib.OfbError):
+        _lib.call('ofb_hermitian_eigh', ctypes.c_int(3), None, None, None)
+    _lib.call('ofb_hermitian_eigh', ctypes.c_int(0), None, None, None)
