@@ -54,9 +54,11 @@ int ofb_memcpy_h2d(void *d_dst, const void *h_src, size_t bytes, void *stream);
 int ofb_memcpy_d2h(void *h_dst, const void *d_src, size_t bytes, void *stream);
 int ofb_memcpy_d2d(void *d_dst, const void *d_src, size_t bytes, void *stream);
 /* Blocking copies between device memory and ORDINARY (pageable) host memory through the
- * library's pinned staging buffers and `threads` worker threads (<= 0: $OFB_COPY_THREADS or half
- * the cores, at most 8), each on its own stream: the CPU side of the staging -- including the
+ * library's pinned staging buffers and `threads` worker threads (<= 0: $OFB_COPY_THREADS or the
+ * cores, at most 16), each on its own stream: the CPU side of the staging -- including the
  * first touch of freshly allocated destination pages -- runs in parallel and overlaps the DMA.
+ * device < 0: the calling thread's current device.  Work queued earlier on other streams is NOT
+ * waited for: synchronise the producing stream first.
  * What numpy.ndarray results of the reference's calls cost to hand over at 2^28 amplitudes or
  * 7e8 non-zeros (linalg/linear_qubit_operator.py:74-148, linalg/sparse_tools.py:136-194). */
 int ofb_copy_h2d_staged(void *d_dst, const void *h_src, size_t bytes, int device, int threads);

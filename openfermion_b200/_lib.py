@@ -226,31 +226,60 @@ class DeviceBuffer:
             pass
 
 
+STAGED_COPY_BYTES = 64 << 20  # host arrays at least this large move through csrc/hostcopy.cu
+
+
+def _staged(nbytes):
+    return nbytes >= STAGED_COPY_BYTES and os.environ.get('OFB_STAGED_COPY', '1') != '0'
+
+
+def copy_h2d(dev_ptr, array, stream=None):
+    """Blocking copy of a contiguous numpy array to device memory (staged above 64 MB)."""
+    if not array.nbytes:
+        return
+    if _staged(array.nbytes):
+        call('ofb_stream_sync', c_void_p(stream))  # earlier users of the destination are done
+        call('ofb_copy_h2d_staged', c_void_p(dev_ptr), ptr(array), c_size_t(array.nbytes), c_int(-1), c_int(0))
+        return
+    call('ofb_memcpy_h2d', c_void_p(dev_ptr), ptr(array), c_size_t(array.nbytes), c_void_p(stream))
+    call('ofb_stream_sync', c_void_p(stream))
+
+
+def copy_d2h(array, dev_ptr, stream=None):
+    """Blocking copy of device memory into a contiguous numpy array (staged above 64 MB)."""
+    if not array.nbytes:
+        return
+    if _staged(array.nbytes):
+        call('ofb_stream_sync', c_void_p(stream))  # the producer of the source is done
+        call('ofb_copy_d2h_staged', ptr(array), c_void_p(dev_ptr), c_size_t(array.nbytes), c_int(-1), c_int(0))
+        return
+    call('ofb_memcpy_d2h', ptr(array), c_void_p(dev_ptr), c_size_t(array.nbytes), c_void_p(stream))
+    call('ofb_stream_sync', c_void_p(stream))
+
+
 def to_device(array, stream=None):
     array = numpy.ascontiguousarray(array)
     buf = DeviceBuffer(array.nbytes)
-    if array.nbytes:
-        call('ofb_memcpy_h2d', c_void_p(buf.ptr), ptr(array), c_size_t(array.nbytes), c_void_p(stream))
-        call('ofb_stream_sync', c_void_p(stream))
+    copy_h2d(buf.ptr, array, stream)
     return buf
 
 
 def to_host(buf, shape, dtype, byte_offset=0, stream=None):
     out = numpy.empty(shape, dtype=dtype)
-    if out.nbytes:
-        call('ofb_memcpy_d2h', ptr(out), buf.at(byte_offset), c_size_t(out.nbytes), c_void_p(stream))
-        call('ofb_stream_sync', c_void_p(stream))
+    copy_d2h(out, buf.ptr + byte_offset, stream)
     return out
 
 
 def parallel_d2h(pairs, device=0, threads=None, chunk=1 << 27, pretouch=None, staged=None):
     """Device -> host copies of large results into ordinary (pageable, usually untouched) numpy
-    arrays from several host threads, each on its own stream.  `pairs` = [(host array, device
-    pointer)].  A pageable copy stages through the driver's pinned buffer and the CPU copy out of
-    it -- where the first touch (page fault + zeroing) of every destination page happens -- runs
-    in the calling thread; ctypes releases the GIL, so the threads overlap.  Measured on the
-    B200 box (16 cores): 4 GB into fresh memory 0.85 s from one thread."""
+    arrays.  `pairs` = [(host array, device pointer)].  Default (`staged`): the library's own
+    pinned staging buffers and worker threads (csrc/hostcopy.cu, ofb_copy_d2h_staged) -- the first
+    touch of every destination page happens in the workers' memcpy, in parallel with the DMA;
+    14.9 GB in 0.52 s with 16 workers against 3.6 s for one plain pageable cudaMemcpy.
+    `staged=False` (or OFB_STAGED_COPY=0) is the earlier path: Python threads, each with its own
+    stream, a memset first touch (`pretouch`) and a pageable copy per 128 MB piece (0.96 s)."""
     import concurrent.futures
+    requested = threads or 0  # staged copies: 0 lets the library choose (the cores, at most 16)
     threads = threads or int(os.environ.get('OFB_D2H_THREADS', '0')) or max(1, min(8, (os.cpu_count() or 2) // 2))
     if pretouch is None:
         pretouch = os.environ.get('OFB_D2H_PRETOUCH', '1') == '1'
@@ -269,7 +298,7 @@ def parallel_d2h(pairs, device=0, threads=None, chunk=1 << 27, pretouch=None, st
         if staged:
             # the library's own pinned staging + worker threads (csrc/hostcopy.cu)
             call('ofb_copy_d2h_staged', c_void_p(base), c_void_p(dev_ptr), c_size_t(nbytes), c_int(device),
-                 c_int(threads))
+                 c_int(requested))
             continue
         for off in range(0, nbytes, chunk):
             jobs.append((base + off, dev_ptr + off, min(chunk, nbytes - off)))

@@ -876,7 +876,8 @@ int ofb_expectation_host(ofb_plan *p, const void *h_state, double *h_out_ri) {
     const size_t bytes = ((size_t)1 << p->n_qubits) * 16;
     int rc = ensure_stage(p, bytes, 0);
     if (rc) return rc;
-    OFB_CUDA(cudaMemcpyAsync(p->d_stage_in, h_state, bytes, cudaMemcpyHostToDevice, 0));
+    rc = host_to_device(p->d_stage_in, h_state, bytes, p->device, 0);
+    if (rc) return rc;
     return launch_expectation(p, p->d_stage_in, h_out_ri, 0);
 }
 
@@ -896,6 +897,10 @@ int ofb_diagonal_host(ofb_plan *p, double *h_out) {
     if (rc) return rc;
     rc = launch_diagonal(p, (double *)p->d_stage_out, 0);
     if (rc) return rc;
+    if (staged_ok(bytes)) {
+        OFB_CUDA(cudaStreamSynchronize(0));
+        return staged_copy(p->d_stage_out, h_out, bytes, false, p->device, 0);
+    }
     OFB_CUDA(cudaMemcpyAsync(h_out, p->d_stage_out, bytes, cudaMemcpyDeviceToHost, 0));
     OFB_CUDA(cudaStreamSynchronize(0));
     return OFB_OK;

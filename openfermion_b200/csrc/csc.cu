@@ -251,7 +251,7 @@ int ofb_csc_fill(ofb_plan *p, void *d_indptr, void *d_indices, void *d_data, int
         else
             k_convert_ptr<int64_t><<<pgrid, 256, 0, s>>>(p->d_colptr, (int64_t)dim + 1, (int64_t *)d_indptr);
         OFB_LAUNCH_CHECK();
-        return csc_tile_fill(p, words, p->d_bitmap, p->d_bitmap + (size_t)words * dim, p->d_colptr,
+        return csc_tile_fill(p, words, p->d_bitmap, p->d_bitmap + (size_t)words * dim, d_indptr,
                              d_indices, d_data, index_bits, s);
     }
 #define OFB_FILL(ZZ, II)                                                                       \

@@ -132,7 +132,7 @@ k_csc_tile(const Chunk *__restrict__ chunks, const uint4 *__restrict__ slices, u
            const uint8_t *__restrict__ group_slow, const ScatterRow *__restrict__ rows,
            const GroupDesc *__restrict__ groups, int n, uint64_t dim, uint32_t words,
            uint32_t *__restrict__ bitmap, const uint32_t *__restrict__ prefix,
-           const int64_t *__restrict__ colptr, I *__restrict__ indices, double2 *__restrict__ data) {
+           const I *__restrict__ colptr, I *__restrict__ indices, double2 *__restrict__ data) {
     __shared__ CscStage sbuf[2];
     __shared__ uint32_t s_sib[2][CHUNK_MAX_SEGS][32];
     __shared__ uint32_t s_group[2][CHUNK_MAX_SEGS];
@@ -231,7 +231,7 @@ k_csc_tile(const Chunk *__restrict__ chunks, const uint4 *__restrict__ slices, u
                 bool nz[QW];
                 int32_t rank[QW];
                 uint32_t bm[QW], pf[QW];
-                int64_t cp[QW];
+                I cp[QW];
 #pragma unroll
                 for (int q = 0; q < QW; ++q) {
                     const int r = r0 + q;
@@ -254,7 +254,7 @@ k_csc_tile(const Chunk *__restrict__ chunks, const uint4 *__restrict__ slices, u
                     const int r = r0 + q;
                     if (FILL && nz[q]) {
                         const uint64_t col = (uint64_t)(c0 + r * TB);
-                        const int64_t pos = cp[q] + pf[q] + __popc(bm[q] & ((1u << (rank[q] & 31)) - 1u));
+                        const int64_t pos = (int64_t)cp[q] + pf[q] + __popc(bm[q] & ((1u << (rank[q] & 31)) - 1u));
                         indices[pos] = (I)(col ^ (uint64_t)x);
                         data[pos] = make_double2(vr[r], vi[r]);
                     }
@@ -329,7 +329,7 @@ static uint32_t csc_slice_count(const ofb_plan *p, bool fill, double bytes_per_t
     const double resident = 148.0 * 6.0;
     double s = std::ceil(4.0 * resident / tiles);  // (1) at least ~4 waves of CTAs
     if (fill && bytes_per_tile > 0.0) s = std::max(s, std::ceil(resident * bytes_per_tile / 17e6));  // (2)
-    s = std::min(s, std::floor((double)G / 3.0));  // a slice keeps >= 3 groups: staging + prologue per CTA
+    s = std::min(s, std::floor((double)G / 2.0));  // a slice keeps >= 2 groups: staging + prologue per CTA
     return (uint32_t)std::min<double>(std::max(s, 1.0), 4096.0);
 }
 
@@ -383,8 +383,8 @@ int csc_tile_count(ofb_plan *p, uint32_t words, uint32_t *bitmap, uint32_t *pref
 #define OFB_TILE(II)                                                                              \
     k_csc_tile<false, II, int32_t><<<grid, TB, 0, s>>>(                                           \
         p->d_chunks, p->d_count_slices, n_slices, p->d_segs, p->d_seg_group, p->d_zc, p->d_zc_im, p->d_sib,       \
-        p->d_group_slow, p->d_rows, p->d_groups, p->n_qubits, dim, words, bitmap, prefix, nullptr, \
-        (int32_t *)nullptr, nullptr)
+        p->d_group_slow, p->d_rows, p->d_groups, p->n_qubits, dim, words, bitmap, prefix,         \
+        (const int32_t *)nullptr, (int32_t *)nullptr, nullptr)
     if (p->has_imag) OFB_TILE(true); else OFB_TILE(false);
 #undef OFB_TILE
     OFB_LAUNCH_CHECK();
@@ -393,7 +393,7 @@ int csc_tile_count(ofb_plan *p, uint32_t words, uint32_t *bitmap, uint32_t *pref
     return OFB_OK;
 }
 
-int csc_tile_fill(ofb_plan *p, uint32_t words, uint32_t *bitmap, uint32_t *prefix, const int64_t *colptr,
+int csc_tile_fill(ofb_plan *p, uint32_t words, uint32_t *bitmap, uint32_t *prefix, const void *d_indptr,
                   void *d_indices, void *d_data, int index_bits, cudaStream_t s) {
     const uint64_t dim = 1ull << p->n_qubits;
     const double bytes_per_tile = (double)p->csc_nnz * (16.0 + index_bits / 8) / (double)(dim / TTILE);
@@ -405,7 +405,7 @@ int csc_tile_fill(ofb_plan *p, uint32_t words, uint32_t *bitmap, uint32_t *prefi
     k_csc_tile<true, II, TT><<<grid, TB, 0, s>>>(                                                 \
         p->d_chunks, p->d_fill_slices, n_slices, p->d_segs, p->d_seg_group, p->d_zc, p->d_zc_im, p->d_sib,       \
         p->d_group_slow, p->d_rows, p->d_groups, p->n_qubits, dim, words, bitmap, prefix,         \
-        colptr, (TT *)d_indices, (double2 *)d_data)
+        (const TT *)d_indptr, (TT *)d_indices, (double2 *)d_data)
     if (index_bits == 32) {
         if (p->has_imag) OFB_TILE(true, int32_t); else OFB_TILE(false, int32_t);
     } else {

@@ -9,7 +9,7 @@
 // is ours: a few worker threads, each with its own stream and two pinned buffers, move disjoint
 // chunks -- the CPU side (memcpy between the caller's pages and pinned memory, page faults
 // included) runs in parallel and overlaps the DMA of the other buffer.  The pinned buffers are
-// allocated once per process (128 MB for 8 workers) and reused.
+// allocated once per process (16 MB per worker, at most 16 workers) and reused.
 #include <algorithm>
 #include <cstring>
 #include <mutex>
@@ -59,7 +59,9 @@ int worker_count(size_t bytes, int threads) {
         const char *env = getenv("OFB_COPY_THREADS");
         threads = env ? atoi(env) : 0;
     }
-    if (threads <= 0) threads = (int)std::min<unsigned>(8u, std::max(1u, std::thread::hardware_concurrency() / 2));
+    // measured on the 16-core B200 box: 4.3 GB host -> device 0.41 s plain, 0.12 s with 8 workers,
+    // 0.094 s with 16; 14.9 GB device -> host into fresh pages 3.6 s plain, 0.86 s / 0.52 s
+    if (threads <= 0) threads = (int)std::min<unsigned>(16u, std::max(1u, std::thread::hardware_concurrency()));
     threads = std::min(threads, MAX_WORKERS);
     return (int)std::max<size_t>(1, std::min<size_t>((size_t)threads, (bytes + STAGE_BYTES - 1) / STAGE_BYTES));
 }
@@ -69,6 +71,7 @@ int worker_count(size_t bytes, int threads) {
 // Blocking.  `d` device pointer, `h` pageable (or any) host pointer.
 int staged_copy(void *d, void *h, size_t bytes, bool to_device, int device, int threads) {
     if (bytes == 0) return OFB_OK;
+    if (device < 0) OFB_CUDA(cudaGetDevice(&device));  // the calling thread's current device
     std::lock_guard<std::mutex> lock(g_copy_mu);
     const int T = worker_count(bytes, threads);
     const size_t n_chunks = (bytes + STAGE_BYTES - 1) / STAGE_BYTES;

@@ -259,13 +259,14 @@ int csc_exact_fill(ofb_plan *plan, const int64_t *d_colptr, void *d_indices, voi
                    int index_bits, cudaStream_t s);
 // csc_tile.cu: tiled count / fill passes for Pauli plans (term tables shared by 1 024 columns)
 // hostcopy.cu: blocking copy between a device pointer and pageable host memory through pinned
-// staging buffers and worker threads (threads <= 0: OFB_COPY_THREADS or half the cores, at most 8)
+// staging buffers and worker threads (threads <= 0: OFB_COPY_THREADS or the cores, at most 16)
 int staged_copy(void *d, void *h, size_t bytes, bool to_device, int device, int threads);
 bool csc_tile_ok(const ofb_plan *plan);
 int csc_tile_count(ofb_plan *plan, uint32_t words, uint32_t *bitmap, uint32_t *prefix, int64_t *counts,
                    cudaStream_t s);
 int csc_tile_fill(ofb_plan *plan, uint32_t words, uint32_t *bitmap, uint32_t *prefix,
-                  const int64_t *colptr, void *d_indices, void *d_data, int index_bits, cudaStream_t s);
+                  const void *d_indptr /* index_bits wide, already converted */, void *d_indices,
+                  void *d_data, int index_bits, cudaStream_t s);
 // shared reduction helper (vec.cu): sums `count` rows of `width` doubles
 int reduce_partials(const double *d_partials, int64_t count, int width, double *d_out,
                     cudaStream_t s);

@@ -69,18 +69,13 @@ class _ColumnBlock:
         if host.ndim == 1:
             host = host.reshape(-1, 1)
         k = host.shape[1]
-        _lib.call('ofb_memcpy_h2d', c_void_p(self.col(0)), _lib.ptr(host),
-                  _lib.c_size_t(host.nbytes), c_void_p(None))
-        _lib.call('ofb_stream_sync', c_void_p(None))
+        _lib.copy_h2d(self.col(0), host)
         self.count = k
 
     def download(self, k0=0, k1=None):
         k1 = self.count if k1 is None else k1
         out = numpy.empty((self.dim, k1 - k0), dtype=numpy.complex128, order='F')
-        if out.size:
-            _lib.call('ofb_memcpy_d2h', _lib.ptr(out), c_void_p(self.col(k0)),
-                      _lib.c_size_t(out.nbytes), c_void_p(None))
-            _lib.call('ofb_stream_sync', c_void_p(None))
+        _lib.copy_d2h(out, self.col(k0))
         return out
 
     def free(self):

@@ -84,16 +84,12 @@ def copy(n, src, dst, stream=None):
 
 def upload(host_vec, dst, stream=None):
     host_vec = numpy.ascontiguousarray(host_vec, dtype=numpy.complex128)
-    _lib.call('ofb_memcpy_h2d', c_void_p(dst), _lib.ptr(host_vec), ctypes.c_size_t(host_vec.nbytes),
-              c_void_p(stream))
-    _lib.call('ofb_stream_sync', c_void_p(stream))
+    _lib.copy_h2d(dst, host_vec, stream)
 
 
 def download(n, src, stream=None):
     out = numpy.empty(n, dtype=numpy.complex128)
-    _lib.call('ofb_memcpy_d2h', _lib.ptr(out), c_void_p(src), ctypes.c_size_t(out.nbytes),
-              c_void_p(stream))
-    _lib.call('ofb_stream_sync', c_void_p(stream))
+    _lib.copy_d2h(out, src, stream)
     return out
 
 

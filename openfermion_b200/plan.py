@@ -149,7 +149,7 @@ class PauliPlan:
         return out
 
     # CSC outputs at least this large leave the device through _lib.parallel_d2h
-    PARALLEL_D2H_BYTES = int(os.environ.get('OFB_PARALLEL_D2H_BYTES', str(1 << 30)))
+    PARALLEL_D2H_BYTES = int(os.environ.get('OFB_PARALLEL_D2H_BYTES', str(1 << 26)))
     # term-order sums are bit-identical to the reference up to this many triplets per column
     # (libstdc++'s std::sort is a stable insertion sort up to 16 elements)
     STABLE_SORT_LIMIT = 16
@@ -182,9 +182,9 @@ class PauliPlan:
         indices = numpy.empty(nnz.value, dtype=idx_dtype)
         data = numpy.empty(nnz.value, dtype=numpy.complex128)
         if indices.nbytes + data.nbytes >= self.PARALLEL_D2H_BYTES:
-            # gigabytes of output (config 2: 15 GB): fill on the device, then copy out from
-            # several host threads -- a single pageable copy into fresh memory runs at ~5 GB/s
-            # because the first touch of every destination page happens inside it
+            # large output (config 2: 15 GB): fill on the device, then staged copies from several
+            # worker threads -- a single pageable copy into fresh memory runs at ~5 GB/s because
+            # the first touch of every destination page happens inside it
             d_indptr = _lib.DeviceBuffer(indptr.nbytes)
             d_indices = _lib.DeviceBuffer(indices.nbytes)
             d_data = _lib.DeviceBuffer(data.nbytes)
