@@ -350,8 +350,9 @@ def run_single(args):
         'clocks': clocks,
         'e2e': {'value': e2e_value, 'unit': UNIT, 'h2d_bytes_per_step': dim * 16,
                 'd2h_bytes_per_step': dim * 16, 'steps': e2e_steps, 'ms_per_step': 1e3 * e2e_seconds / e2e_steps,
-                'path': 'LinearQubitOperator.matvec(numpy array in pageable host memory): H2D, kernel, '
-                        'D2H of output slabs behind the kernel (ofb_apply_host)'},
+                'path': 'LinearQubitOperator.matvec(numpy array in pageable host memory): staged H2D in 8 slabs '
+                        '(slab-local x-groups start behind each slab), remaining groups, staged D2H of output '
+                        'slabs behind the kernel (ofb_apply_host, csrc/hostcopy.cu)'},
         'gpu_launches': int(launches),
         'roofline': {'bound': bound, 'achieved': achieved, 'peak': peak, 'unit': 'GB/s',
                      'frac': achieved / peak, 'traffic': traffic, 'peak_source': peak_src,

@@ -822,9 +822,21 @@ int ofb_apply_host(ofb_plan *p, const void *h_in, void *h_out, int ncols) {
         for (int k = 0; k < HOST_SLABS; ++k)
             OFB_CUDA(cudaEventCreateWithFlags(&p->slab_done[k], cudaEventDisableTiming));
     }
+    // Groups whose x mask has no bit among the top log2(slabs) index bits gather inside their own
+    // slab: their share of the work (62 % of the 28-qubit molecular table) starts as soon as that
+    // slab of the INPUT has arrived, while the worker threads copy the next slab; the remaining
+    // groups follow as accumulate launches once the whole input is on the device.
+    int64_t g_local = 0;
+    if (slabs > 1 && staged_ok(col_bytes / slabs) && !(getenv("OFB_H2D_OVERLAP") && getenv("OFB_H2D_OVERLAP")[0] == '0')) {
+        const uint64_t limit = (uint64_t)dim / (uint64_t)slabs;
+        g_local = std::lower_bound(p->h_group_x.begin(), p->h_group_x.end(), limit) - p->h_group_x.begin();
+    }
     for (int c = 0; c < ncols; ++c) {
-        rc = host_to_device(p->d_stage_in, (const char *)h_in + c * col_bytes, col_bytes, p->device, s);
-        if (rc) return rc;
+        const char *src_col = (const char *)h_in + c * col_bytes;
+        if (g_local == 0) {
+            rc = host_to_device(p->d_stage_in, src_col, col_bytes, p->device, s);
+            if (rc) return rc;
+        }
         if (slabs == 1) {
             rc = launch_apply(p, p->d_stage_in, p->d_stage_out, p->n_qubits, 0, 0, p->n_groups, 0, s);
             if (rc) return rc;
@@ -839,8 +851,26 @@ int ofb_apply_host(ofb_plan *p, const void *h_in, void *h_out, int ncols) {
             continue;
         }
         const uint64_t per = tiles / slabs;
-        for (int k = 0; k < slabs; ++k) {  // all launches are queued before the first copy is issued
-            rc = launch_apply_slab(p, p->d_stage_in, p->d_stage_out, p->n_qubits, k * per, per, s);
+        if (g_local > 0) {
+            OFB_CUDA(cudaStreamSynchronize(s));  // the previous column's kernels are done with stage_in
+            const size_t in_slab = col_bytes / slabs;
+            for (int k = 0; k < slabs; ++k) {
+                rc = staged_copy((char *)p->d_stage_in + k * in_slab, const_cast<char *>(src_col) + k * in_slab, in_slab,
+                                 true, p->device, 0);
+                if (!rc)
+                    rc = launch_apply_impl<0>(p, p->d_stage_in, p->d_stage_out, p->n_qubits, 0, 0, g_local, 0, nullptr,
+                                              s, k * per, per);
+                if (rc) return rc;
+                if (g_local == p->n_groups) OFB_CUDA(cudaEventRecord(p->slab_done[k], s));  // slab complete
+            }
+        }
+        for (int k = 0; k < slabs && !(g_local > 0 && g_local == p->n_groups); ++k) {
+            // all launches are queued before the first output copy is issued
+            if (g_local > 0)
+                rc = launch_apply_impl<0>(p, p->d_stage_in, p->d_stage_out, p->n_qubits, 0, g_local, p->n_groups, 1,
+                                          nullptr, s, k * per, per);
+            else
+                rc = launch_apply_slab(p, p->d_stage_in, p->d_stage_out, p->n_qubits, k * per, per, s);
             if (rc) return rc;
             OFB_CUDA(cudaEventRecord(p->slab_done[k], s));
         }

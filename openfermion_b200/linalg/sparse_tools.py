@@ -13,7 +13,7 @@ import numpy
 import scipy.sparse
 import scipy.sparse.linalg
 
-from openfermion_b200 import ops, sectors
+from openfermion_b200 import _lib, ops, sectors
 from openfermion_b200.compiler import compile_fermion_terms, compile_qubit_operator
 from openfermion_b200.linalg import krylov
 from openfermion_b200.linalg.linear_qubit_operator import (LinearQubitOperator,
@@ -233,7 +233,25 @@ def expectation(operator, state):
 
 
 def variance(operator, state):
-    """<H^2> - <H>^2 (sparse_tools.py:674-690)."""
+    """<H^2> - <H>^2 (sparse_tools.py:674-690).  For the matrix-free operators the reference's
+    `operator**2` is scipy's power operator, i.e. two host matvecs plus a third for <H>; here the
+    state is uploaded once and w = H v, u = H w, <v|u> - <v|w>^2 are formed on the device."""
+    if (isinstance(state, numpy.ndarray) and state.ndim == 1
+            and isinstance(operator, (LinearQubitOperator, SectorLinearQubitOperator))):
+        if state.size != operator.shape[1]:
+            raise ValueError('Dimension mismatch')
+        dev_op = krylov.as_device_operator(operator)
+        n = dev_op.dim
+        v = _lib.to_device(numpy.ascontiguousarray(state, dtype=numpy.complex128))
+        w = _lib.DeviceBuffer(n * krylov.C128)
+        u = _lib.DeviceBuffer(n * krylov.C128)
+        try:
+            dev_op.apply(v.ptr, w.ptr)
+            dev_op.apply(w.ptr, u.ptr)
+            return krylov.dotc(n, v.ptr, u.ptr) - krylov.dotc(n, v.ptr, w.ptr) ** 2
+        finally:
+            for buf in (v, w, u):
+                buf.free()
     return expectation(operator**2, state) - expectation(operator, state) ** 2
 
 

@@ -49,3 +49,34 @@ def test_matvec_above_the_switch_equals_plain_copies(monkeypatch):
     assert numpy.array_equal(got, want)
     # two consecutive calls reuse the staging buffers
     assert numpy.array_equal(lin * v, want)
+
+
+def _shifted(op, shift):
+    from openfermion_b200.ops import QubitOperator
+    out = QubitOperator()
+    out.terms.update({tuple((q + shift, a) for q, a in key): value for key, value in op.terms.items()})
+    return out
+
+
+@pytest.mark.parametrize('case', ['mixed', 'all_groups_inside_a_slab'])
+def test_input_slabs_overlapping_the_kernel(case, monkeypatch):
+    # 25 qubits: 512 MB per vector, 64 MB slabs -> ofb_apply_host starts the groups that gather
+    # inside a slab while the next input slab is still being copied (OFB_H2D_OVERLAP=0: one copy,
+    # then the kernels).  Both orders must give the same bytes as the plain-copy path.
+    n = 25
+    if case == 'mixed':
+        op = hamiltonians.random_pauli_sum(n, 40, 11, False)
+    else:  # qubits 3..24 = index bits 21..0: no x mask touches the three slab bits
+        op = _shifted(hamiltonians.random_pauli_sum(n - 3, 30, 12, True), 3)
+    rng = numpy.random.default_rng(4)
+    v = rng.normal(size=1 << n) + 1j * rng.normal(size=1 << n)
+    got = LinearQubitOperator(op, n) * v
+    monkeypatch.setenv('OFB_H2D_OVERLAP', '0')
+    assert numpy.array_equal(LinearQubitOperator(op, n) * v, got)
+    monkeypatch.setenv('OFB_STAGED_COPY', '0')
+    assert numpy.array_equal(LinearQubitOperator(op, n) * v, got)
+    # sampled outputs against the oracle's reference-order term sum
+    import pauli_oracle as po
+    idx = rng.integers(0, 1 << n, size=64)
+    want = po.matvec_sampled(op.terms, n, v, idx)
+    assert numpy.max(numpy.abs(got[idx] - want)) <= 1e-12 * numpy.max(numpy.abs(want))

@@ -111,6 +111,21 @@ def test_variance_known_answers():
     assert abs(variance(lin, v) - variance(mat, v)) < 1e-13
 
 
+def test_variance_matrix_free_on_the_device_equals_the_oracle():
+    # the device-resident <v|H(Hv)> - <v|Hv>^2 of the matrix-free operators against the formula of
+    # sparse_tools.py:674-690 evaluated with the oracle's matvec; complex, non-Hermitian sum too
+    rng = numpy.random.default_rng(8)
+    for op, n in ((hamiltonians.molecular_jw(7, seed=5), 14), (hamiltonians.random_pauli_sum(11, 90, 3, True), 11)):
+        v = rng.normal(size=1 << n) + 1j * rng.normal(size=1 << n)
+        v /= numpy.linalg.norm(v)
+        w = po.matvec(op.terms, n, v)
+        want = numpy.vdot(v, po.matvec(op.terms, n, w)) - numpy.vdot(v, w) ** 2
+        got = variance(LinearQubitOperator(op, n), v)
+        assert abs(got - want) <= 1e-12 * max(1.0, abs(want))
+    with pytest.raises(ValueError):
+        variance(LinearQubitOperator(hamiltonians.hubbard_jw(2, 2), 8), numpy.ones(17))
+
+
 # ---- golden vectors from the real reference ------------------------------------------
 @pytest.mark.parametrize('case', helpers.qubit_cases(), ids=lambda c: c.name)
 def test_golden_matvec_expectation_diagonal(case):
