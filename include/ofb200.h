@@ -193,9 +193,11 @@ int ofb_csr_matvec(int64_t n_rows, const void *d_indptr, const void *d_indices, 
  * linalg/sparse_tools.py:578).  All vectors complex128 of length n. Scalars that
  * come back are written to host memory after a stream synchronise.
  * Threading: the reductions (dotc, nrm2, maxabs, multi_dotc, davidson_correction) share ONE
- * scratch buffer and one pinned result buffer per device; call them from one host thread and
- * one stream at a time per device (as a numpy caller of the reference would: its matvec is
- * single-threaded).  The plan / sector reductions (expectation) are per object, same rule. */
+ * scratch buffer and one pinned result buffer per device; each call holds a per-device lock from
+ * its first kernel to the stream synchronisation that ends it, so calls from several host threads
+ * or streams serialise.  The plan / sector reductions (expectation) use per-object scratch: one
+ * thread and stream at a time per plan (as a numpy caller of the reference: its matvec is
+ * single-threaded). */
 int ofb_vec_dotc(int64_t n, const void *d_x, const void *d_y, double *h_out_ri, void *stream);
 int ofb_vec_nrm2(int64_t n, const void *d_x, double *h_out, void *stream);
 int ofb_vec_maxabs(int64_t n, const void *d_x, double *h_out, void *stream);

@@ -41,18 +41,32 @@ struct CscStage {
     TermZC im[CHUNK_MAX_TERMS + 8];
 };
 
+struct __align__(16) CscSlice {
+    uint32_t ch0, ch1, seg0, seg1;  // chunks and segments of the slice (whole groups)
+    uint32_t term0, term1, pad0, pad1;  // absolute term range
+    Chunk first;                        // chunks[ch0]: saves the CTA one dependent load
+};
+
 __device__ __forceinline__ void csc_cp16(void *smem, const void *gmem) {
     uint32_t sa = (uint32_t)__cvta_generic_to_shared(smem);
     asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(sa), "l"(gmem) : "memory");
 }
 
+// Stages the part of chunk `ck` that belongs to the slice: segments [seg0, seg1) and terms
+// [term0, term1) (absolute indices), at their usual positions inside the buffer.  A slice of 2-3
+// groups does not pay for the 16 segments / 256 terms of a whole chunk.
 __device__ __forceinline__ void csc_stage(CscStage &b, const Chunk ck, const Segment *__restrict__ segs,
                                           const TermZC *__restrict__ zc_re, const TermZC *__restrict__ zc_im,
-                                          bool has_imag) {
+                                          bool has_imag, uint32_t seg0, uint32_t seg1, uint32_t term0,
+                                          uint32_t term1) {
+    const uint32_t sa = max(ck.seg_begin, seg0) - ck.seg_begin;
+    const uint32_t sb = min(ck.seg_begin + ck.seg_count, seg1) - ck.seg_begin;
     const char *gs = (const char *)(segs + ck.seg_begin);
     char *ss = (char *)b.segs;
-    for (uint32_t u = threadIdx.x; u < ck.seg_count * 2; u += TB) csc_cp16(ss + u * 16, gs + u * 16);
-    for (uint32_t u = threadIdx.x; u < ck.term_count; u += TB) {
+    for (uint32_t u = 2 * sa + threadIdx.x; u < 2 * sb; u += TB) csc_cp16(ss + u * 16, gs + u * 16);
+    const uint32_t ta = max(ck.term_begin, term0) - ck.term_begin;
+    const uint32_t tb = min(ck.term_begin + ck.term_count, term1) - ck.term_begin;
+    for (uint32_t u = ta + threadIdx.x; u < tb; u += TB) {
         csc_cp16(&b.re[u], zc_re + ck.term_begin + u);
         if (has_imag) csc_cp16(&b.im[u], zc_im + ck.term_begin + u);
     }
@@ -122,10 +136,10 @@ __device__ __noinline__ double2 csc_group_rows(const ScatterRow *__restrict__ ro
 // blockIdx.x = tile * n_slices + slice: a tile of 1 024 columns and a slice of the group list
 // (whole groups in x order; see csc_slice_count).  The slices of a tile are neighbours in launch
 // order, so the tiles being written at any time are few.
-// slice = (first chunk, end chunk, first segment, end segment).
+// slice = (first chunk, end chunk, first segment, end segment, first term, end term).
 template <bool FILL, bool HAS_IMAG, typename I>
 __global__ void __launch_bounds__(TB, 6)
-k_csc_tile(const Chunk *__restrict__ chunks, const uint4 *__restrict__ slices, uint32_t n_slices,
+k_csc_tile(const Chunk *__restrict__ chunks, const CscSlice *__restrict__ slices, uint32_t n_slices,
            const Segment *__restrict__ segs,
            const uint32_t *__restrict__ seg_group, const TermZC *__restrict__ zc_re,
            const TermZC *__restrict__ zc_im, const uint32_t *__restrict__ sib,
@@ -144,25 +158,29 @@ k_csc_tile(const Chunk *__restrict__ chunks, const uint4 *__restrict__ slices, u
 #pragma unroll
     for (int r = 0; r < TR; ++r) vr[r] = vi[r] = 0.0;
 
-    auto stage_aux = [&](int buf, const Chunk ck) {  // group ids and sibling rows of the chunk's segments
-        for (uint32_t q = 0; q < ck.seg_count; ++q) {
+    const CscSlice slice = slices[blockIdx.x - tile * n_slices];
+    const uint32_t ch0 = slice.ch0, ch1 = slice.ch1, seg0 = slice.seg0, seg1 = slice.seg1;
+    const uint32_t term0 = slice.term0, term1 = slice.term1;
+
+    auto stage_aux = [&](int buf, const Chunk ck) {  // group ids and sibling rows of the slice's segments
+        const uint32_t qa = max(ck.seg_begin, seg0) - ck.seg_begin;
+        const uint32_t qb = min(ck.seg_begin + ck.seg_count, seg1) - ck.seg_begin;
+        for (uint32_t q = qa; q < qb; ++q) {
             const uint32_t g = seg_group[ck.seg_begin + q];
             if (tid == 0) s_group[buf][q] = g;
             if (tid < 32) s_sib[buf][q][tid] = tid < (uint32_t)n ? sib[(size_t)g * n + tid] : 0u;
         }
     };
 
-    const uint4 slice = slices[blockIdx.x - tile * n_slices];
-    const uint32_t ch0 = slice.x, ch1 = slice.y, seg0 = slice.z, seg1 = slice.w;
-    Chunk cur = chunks[ch0];
+    Chunk cur = slice.first;
     Chunk nxt = ch0 + 1 < ch1 ? chunks[ch0 + 1] : cur;
-    csc_stage(sbuf[0], cur, segs, zc_re, zc_im, HAS_IMAG);
+    csc_stage(sbuf[0], cur, segs, zc_re, zc_im, HAS_IMAG, seg0, seg1, term0, term1);
     stage_aux(0, cur);
     for (uint32_t cc = ch0; cc < ch1; ++cc) {
         const uint32_t c = cc - ch0;  // buffer parity
         Chunk after = nxt;
         if (cc + 1 < ch1) {
-            csc_stage(sbuf[(c + 1) & 1], nxt, segs, zc_re, zc_im, HAS_IMAG);
+            csc_stage(sbuf[(c + 1) & 1], nxt, segs, zc_re, zc_im, HAS_IMAG, seg0, seg1, term0, term1);
             stage_aux((c + 1) & 1, nxt);
             if (cc + 2 < ch1) after = chunks[cc + 2];
             asm volatile("cp.async.wait_group 1;\n" ::: "memory");
@@ -312,9 +330,10 @@ int csc_tile_prepare(ofb_plan *p) {
 //     stores and is complete only if it stays in L2 until the last of them.  With one CTA per
 //     tile the 888 resident CTAs have their whole output open at once (14.9 GB at config 2): ncu
 //     showed 39 GB written + 35 GB read for those 14.9 GB -- sectors evicted half written and
-//     read back.  With S slices per tile only 888 / S tiles are open; measured on B200 the pass
-//     is fastest when the open output is ~17 MB (config 2: S = 768, 54.9 -> 17.0 ms; 24-qubit
-//     Hubbard: S = 24, 25.9 -> 7.1 ms).  Visiting the groups in ROW order instead (blocks of
+//     read back.  With S slices per tile only 888 / S tiles are open; measured on B200 (with a
+//     CTA staging only its own slice of a chunk) the pass is fastest when the open output is
+//     ~10 MB, down to one group per slice (config 2: S = 1 024, 54.9 -> 15.3 ms; 24-qubit
+//     Hubbard: S = 49 = G, 25.9 -> 6.0 ms).  Visiting the groups in ROW order instead (blocks of
 //     equal high x bits sorted by key ^ c_hi per tile, so that each column advances monotonically)
 //     was built and measured: no gain at S = 1 (51.5 ms: an index sector still waits for 8
 //     entries of its column while the chip writes 165 MB) and slower than x-order slices at equal
@@ -328,12 +347,12 @@ static uint32_t csc_slice_count(const ofb_plan *p, bool fill, double bytes_per_t
     const double tiles = (double)((1ull << p->n_qubits) / TTILE);
     const double resident = 148.0 * 6.0;
     double s = std::ceil(4.0 * resident / tiles);  // (1) at least ~4 waves of CTAs
-    if (fill && bytes_per_tile > 0.0) s = std::max(s, std::ceil(resident * bytes_per_tile / 17e6));  // (2)
-    s = std::min(s, std::floor((double)G / 2.0));  // a slice keeps >= 2 groups: staging + prologue per CTA
+    if (fill && bytes_per_tile > 0.0) s = std::max(s, std::ceil(resident * bytes_per_tile / 10e6));  // (2)
+    s = std::min(s, (double)G);  // at least one group per slice
     return (uint32_t)std::min<double>(std::max(s, 1.0), 4096.0);
 }
 
-static int csc_tile_slices(ofb_plan *p, uint32_t want, uint4 **d_out, uint32_t *n_out) {
+static int csc_tile_slices(ofb_plan *p, uint32_t want, void **d_out, uint32_t *n_out) {
     OFB_TRY
     const uint32_t G = (uint32_t)p->n_groups;
     want = std::min(std::max(want, 1u), G);
@@ -342,7 +361,7 @@ static int csc_tile_slices(ofb_plan *p, uint32_t want, uint4 **d_out, uint32_t *
     std::vector<double> acc(G + 1, 0.0);
     for (uint32_t g = 0; g < G; ++g)
         acc[g + 1] = acc[g] + (double)(p->h_group_begin[g + 1] - p->h_group_begin[g]) + 16.0;
-    std::vector<uint4> slices;
+    std::vector<CscSlice> slices;
     uint32_t g0 = 0;
     for (uint32_t k = 1; k <= want; ++k) {
         // slice k ends at the first group boundary at or after its share of the weight, but
@@ -354,13 +373,15 @@ static int csc_tile_slices(ofb_plan *p, uint32_t want, uint4 **d_out, uint32_t *
             g1 = std::min(std::max(g1, g0 + 1), G - (want - k));
         }
         const uint32_t seg0 = p->h_seg_begin[g0], seg1 = p->h_seg_begin[g1];
-        slices.push_back(make_uint4(p->h_chunk_of_seg[seg0], p->h_chunk_of_seg[seg1 - 1] + 1, seg0, seg1));
+        slices.push_back(CscSlice{p->h_chunk_of_seg[seg0], p->h_chunk_of_seg[seg1 - 1] + 1, seg0, seg1,
+                                  p->h_group_begin[g0], p->h_group_begin[g1], 0u, 0u,
+                                  p->h_chunks[p->h_chunk_of_seg[seg0]]});
         g0 = g1;
     }
     cudaFree(*d_out);
     *d_out = nullptr;
-    OFB_CUDA(cudaMalloc(d_out, slices.size() * sizeof(uint4)));
-    OFB_CUDA(cudaMemcpy(*d_out, slices.data(), slices.size() * sizeof(uint4), cudaMemcpyHostToDevice));
+    OFB_CUDA(cudaMalloc(d_out, slices.size() * sizeof(CscSlice)));
+    OFB_CUDA(cudaMemcpy(*d_out, slices.data(), slices.size() * sizeof(CscSlice), cudaMemcpyHostToDevice));
     *n_out = (uint32_t)slices.size();
     return OFB_OK;
     OFB_CATCH((void)0)
@@ -382,7 +403,7 @@ int csc_tile_count(ofb_plan *p, uint32_t words, uint32_t *bitmap, uint32_t *pref
     const unsigned grid = (unsigned)(dim / TTILE) * n_slices;
 #define OFB_TILE(II)                                                                              \
     k_csc_tile<false, II, int32_t><<<grid, TB, 0, s>>>(                                           \
-        p->d_chunks, p->d_count_slices, n_slices, p->d_segs, p->d_seg_group, p->d_zc, p->d_zc_im, p->d_sib,       \
+        p->d_chunks, (const CscSlice *)p->d_count_slices, n_slices, p->d_segs, p->d_seg_group, p->d_zc, p->d_zc_im, p->d_sib,       \
         p->d_group_slow, p->d_rows, p->d_groups, p->n_qubits, dim, words, bitmap, prefix,         \
         (const int32_t *)nullptr, (int32_t *)nullptr, nullptr)
     if (p->has_imag) OFB_TILE(true); else OFB_TILE(false);
@@ -403,7 +424,7 @@ int csc_tile_fill(ofb_plan *p, uint32_t words, uint32_t *bitmap, uint32_t *prefi
     const unsigned grid = (unsigned)(dim / TTILE) * n_slices;
 #define OFB_TILE(II, TT)                                                                          \
     k_csc_tile<true, II, TT><<<grid, TB, 0, s>>>(                                                 \
-        p->d_chunks, p->d_fill_slices, n_slices, p->d_segs, p->d_seg_group, p->d_zc, p->d_zc_im, p->d_sib,       \
+        p->d_chunks, (const CscSlice *)p->d_fill_slices, n_slices, p->d_segs, p->d_seg_group, p->d_zc, p->d_zc_im, p->d_sib,       \
         p->d_group_slow, p->d_rows, p->d_groups, p->n_qubits, dim, words, bitmap, prefix,         \
         (const TT *)d_indptr, (TT *)d_indices, (double2 *)d_data)
     if (index_bits == 32) {

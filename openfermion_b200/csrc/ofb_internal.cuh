@@ -199,6 +199,7 @@ struct ofb_plan {
     // device tables: gather form (apply / expectation / diagonal)
     std::vector<uint32_t> h_seg_begin;  // n_groups + 1: first segment of each logical group
     std::vector<uint32_t> h_chunk_of_seg;  // chunk holding each segment
+    std::vector<ofb::Chunk> h_chunks;      // host copy of d_chunks (slice descriptors of the CSC passes)
     int64_t n_chunks = 0;
     bool has_imag = false;  // some group has a non-real phased coefficient
     ofb::Chunk *d_chunks = nullptr;
@@ -220,9 +221,9 @@ struct ofb_plan {
     uint32_t *d_seg_group = nullptr;
     uint8_t *d_group_slow = nullptr;
     std::vector<uint8_t> h_group_slow;
-    // slices of the group list for the tiled CSC passes: (first chunk, end chunk, first segment,
-    // end segment) per slice; the count and fill passes choose their own number
-    uint4 *d_count_slices = nullptr, *d_fill_slices = nullptr;
+    // slices of the group list for the tiled CSC passes: chunk, segment and term range per slice;
+    // the count and fill passes choose their own number
+    void *d_count_slices = nullptr, *d_fill_slices = nullptr;  // CscSlice[] (csc_tile.cu)
     uint32_t n_count_slices = 0, n_fill_slices = 0;
     // CSC state between count and fill
     int64_t *d_colptr = nullptr;   // 2^n + 1 exclusive scan of counts

@@ -421,6 +421,7 @@ int ofb_plan_create(int n_qubits, int64_t n_terms, const uint64_t *x_mask, const
         p->h_chunk_of_seg[sidx] = (uint32_t)chunks.size() - 1;
     }
     p->n_chunks = (int64_t)chunks.size();
+    p->h_chunks = chunks;
     // one padding entry so that a software-prefetched load past the end stays in bounds
     zc_re.push_back(TermZC{0, 0.0});
     zc_im.push_back(TermZC{0, 0.0});

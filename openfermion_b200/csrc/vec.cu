@@ -18,6 +18,19 @@ struct DevScratch {
 };
 static DevScratch g_scratch[64];
 static std::mutex g_scratch_mu;
+// The reductions share one scratch buffer and one pinned result buffer per device.  Every entry
+// point that uses them holds this lock from its first kernel to the stream synchronisation that
+// ends it, so calls from several host threads or streams on one device serialise instead of
+// racing on the partial sums.
+static std::mutex g_reduce_mu[64];
+struct ReduceLock {
+    std::unique_lock<std::mutex> lk;
+    ReduceLock() {
+        int dev = 0;
+        if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) dev = 0;
+        lk = std::unique_lock<std::mutex>(g_reduce_mu[dev]);
+    }
+};
 
 double *global_scratch(size_t bytes) {
     int dev = 0;
@@ -348,6 +361,7 @@ extern "C" {
 
 int ofb_vec_dotc(int64_t n, const void *d_x, const void *d_y, double *h_out_ri, void *stream) {
     if (n < 0 || !h_out_ri) return fail(OFB_ERR_INVALID, "bad argument");
+    ReduceLock guard;
     cudaStream_t s = (cudaStream_t)stream;
     unsigned g = rgrid(n);
     double *part = global_scratch((size_t)(2 * g + 2) * sizeof(double));
@@ -361,6 +375,7 @@ int ofb_vec_dotc(int64_t n, const void *d_x, const void *d_y, double *h_out_ri, 
 
 int ofb_vec_nrm2(int64_t n, const void *d_x, double *h_out, void *stream) {
     if (n < 0 || !h_out) return fail(OFB_ERR_INVALID, "bad argument");
+    ReduceLock guard;
     cudaStream_t s = (cudaStream_t)stream;
     unsigned g = rgrid(n);
     double *part = global_scratch((size_t)(g + 1) * sizeof(double));
@@ -377,6 +392,7 @@ int ofb_vec_nrm2(int64_t n, const void *d_x, double *h_out, void *stream) {
 
 int ofb_vec_maxabs(int64_t n, const void *d_x, double *h_out, void *stream) {
     if (n < 0 || !h_out) return fail(OFB_ERR_INVALID, "bad argument");
+    ReduceLock guard;
     cudaStream_t s = (cudaStream_t)stream;
     unsigned g = rgrid(n);
     double *part = global_scratch((size_t)(g + 1) * sizeof(double));
@@ -408,6 +424,7 @@ int ofb_vec_scal(int64_t n, const double *alpha_ri, void *d_x, void *stream) {
 int ofb_vec_multi_dotc(int64_t n, int ncols, const void *d_V, int64_t ld, const void *d_w,
                        double *h_out_ri, void *stream) {
     if (n < 0 || ncols < 0 || !h_out_ri) return fail(OFB_ERR_INVALID, "bad argument");
+    ReduceLock guard;
     cudaStream_t s = (cudaStream_t)stream;
     unsigned g = rgrid(n);
     double *part = global_scratch((size_t)(2 * MD) * (g + 1) * sizeof(double));
@@ -465,6 +482,7 @@ int ofb_vec_lanczos_update(int64_t n, double alpha, double beta, const void *d_v
 int ofb_davidson_correction(int64_t n, const double *d_diag, double lambda, double eps,
                             const void *d_r, const void *d_v, void *d_new, void *stream) {
     if (n <= 0 || !d_diag) return fail(OFB_ERR_INVALID, "bad argument");
+    ReduceLock guard;
     cudaStream_t s = (cudaStream_t)stream;
     unsigned g = rgrid(n);
     double *part = global_scratch((size_t)4 * (g + 1) * sizeof(double));
@@ -476,6 +494,7 @@ int ofb_davidson_correction(int64_t n, const double *d_diag, double lambda, doub
     k_dav_newdir<<<egrid(n), VB, 0, s>>>(n, part + (size_t)4 * g, (const double2 *)d_r,
                                          (const double2 *)d_v, (double2 *)d_new);
     OFB_LAUNCH_CHECK();
+    OFB_CUDA(cudaStreamSynchronize(s));  // the scratch is free again when the lock is released
     return OFB_OK;
 }
 

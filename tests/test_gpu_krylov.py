@@ -290,3 +290,38 @@ def test_ground_state_at_particle_number_matches_dense_sector():
     assert sz0.shape == (36, 36)
     lowest_sz0 = numpy.linalg.eigvalsh(sz0.toarray())[0]
     assert lowest_sz0 >= numpy.linalg.eigvalsh(restricted.toarray())[0] - 1e-10
+
+
+def test_reductions_from_several_host_threads_and_streams():
+    # the vector reductions share one scratch buffer per device; concurrent callers serialise on
+    # a per-device lock instead of racing on the partial sums
+    import concurrent.futures
+    import ctypes
+    from openfermion_b200 import _lib
+    from openfermion_b200.linalg import krylov
+    n = 1 << 18
+    rng = numpy.random.default_rng(21)
+    vectors = [rng.normal(size=n) + 1j * rng.normal(size=n) for _ in range(4)]
+    bufs = [_lib.to_device(v) for v in vectors]
+    want = [(numpy.vdot(v, v), numpy.linalg.norm(v), numpy.max(numpy.abs(v))) for v in vectors]
+
+    def work(k):
+        _lib.call('ofb_set_device', ctypes.c_int(0))
+        stream = ctypes.c_void_p()
+        _lib.call('ofb_stream_create', ctypes.byref(stream))
+        try:
+            for _ in range(50):
+                d = krylov.dotc(n, bufs[k].ptr, bufs[k].ptr, stream.value)
+                nr = krylov.nrm2(n, bufs[k].ptr, stream.value)
+                mx = krylov.maxabs(n, bufs[k].ptr, stream.value)
+                assert abs(d - want[k][0]) <= 1e-12 * abs(want[k][0])
+                assert abs(nr - want[k][1]) <= 1e-12 * want[k][1]
+                assert mx == want[k][2]
+        finally:
+            _lib.call('ofb_stream_destroy', stream)
+        return True
+
+    with concurrent.futures.ThreadPoolExecutor(4) as pool:
+        assert all(pool.map(work, range(4)))
+    for b in bufs:
+        b.free()

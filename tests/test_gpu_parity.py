@@ -229,7 +229,17 @@ def _state(n, seed):
 def test_matvec_and_expectation_vs_c_oracle(name, builder):
     op = builder()
     n = op.n_qubits
-    x, z, c = compiler.compile_qubit_operator(op, n)
+    # the masks handed to the C oracle come from the ORACLE's own fold of the term dict
+    # (pauli_oracle.term_masks, linear_qubit_operator.py:122-134), not from the product compiler,
+    # so a compiler bug cannot cancel out; the compiler's tables are compared too
+    x = numpy.zeros(len(op.terms), dtype=numpy.uint64)
+    z = numpy.zeros(len(op.terms), dtype=numpy.uint64)
+    c = numpy.zeros(len(op.terms), dtype=numpy.complex128)
+    for k, (term, coefficient) in enumerate(op.terms.items()):
+        x[k], z[k], _ = po.term_masks(term, n)
+        c[k] = coefficient
+    cx, cz, cc = compiler.compile_qubit_operator(op, n)
+    assert sorted(zip(x.tolist(), z.tolist(), c.tolist())) == sorted(zip(cx.tolist(), cz.tolist(), cc.tolist()))
     v = _state(n, 7)
     want = c_oracle.matvec(n, x, z, c, v)
     lin = LinearQubitOperator(op, n)
