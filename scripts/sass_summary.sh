@@ -10,3 +10,9 @@ for pat in "k_apply_tileILb1ELi0ELb0ELb1E" "k_apply_tileILb1ELi0ELb0ELb0E" "k_ap
     cuobjdump -sass -fun "$(cuobjdump -elf $LIB 2>/dev/null | grep -o "_ZN3ofb12${pat}[A-Za-z0-9_]*" | head -1)" $LIB 2>/dev/null \
         | grep -E "^\s+/\*[0-9a-f]{4}\*/" | sed -E 's/^\s+\/\*[0-9a-f]+\*\/\s+(@!?U?P[0-9T]+\s+)?([A-Z0-9_]+).*/\2/' | sort | uniq -c | sort -rn | head -24
 done
+for pat in "k_csc_tileILb1ELb0EiE" "k_csc_tileILb0ELb0EiE"; do
+    echo
+    echo "# opcode histogram of $pat (cuobjdump -sass)"
+    cuobjdump -sass -fun "$(cuobjdump -elf $LIB 2>/dev/null | grep -o "_ZN3ofb10${pat}[A-Za-z0-9_]*" | head -1)" $LIB 2>/dev/null \
+        | grep -E "^\s+/\*[0-9a-f]{4}\*/" | sed -E 's/^\s+\/\*[0-9a-f]+\*\/\s+(@!?U?P[0-9T]+\s+)?([A-Z0-9_]+).*/\2/' | sort | uniq -c | sort -rn | head -16
+done
