@@ -157,6 +157,10 @@ k_csc_tile(const Chunk *__restrict__ chunks, const CscSlice *__restrict__ slices
     double vr[TR], vi[TR];
 #pragma unroll
     for (int r = 0; r < TR; ++r) vr[r] = vi[r] = 0.0;
+#ifdef OFB_CSC_EVICT_LAST
+    uint64_t l2_keep;
+    asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(l2_keep));
+#endif
 
     const CscSlice slice = slices[blockIdx.x - tile * n_slices];
     const uint32_t ch0 = slice.ch0, ch1 = slice.ch1, seg0 = slice.seg0, seg1 = slice.seg1;
@@ -273,8 +277,18 @@ k_csc_tile(const Chunk *__restrict__ chunks, const CscSlice *__restrict__ slices
                     if (FILL && nz[q]) {
                         const uint64_t col = (uint64_t)(c0 + r * TB);
                         const int64_t pos = (int64_t)cp[q] + pf[q] + __popc(bm[q] & ((1u << (rank[q] & 31)) - 1u));
+#ifdef OFB_CSC_EVICT_LAST
+                        // partially written sectors should outlive the lookup traffic in L2
+                        const I row = (I)(col ^ (uint64_t)x);
+                        if (sizeof(I) == 4)
+                            asm volatile("st.global.L2::cache_hint.b32 [%0], %1, %2;" ::"l"(indices + pos), "r"((uint32_t)row), "l"(l2_keep) : "memory");
+                        else
+                            asm volatile("st.global.L2::cache_hint.b64 [%0], %1, %2;" ::"l"(indices + pos), "l"((uint64_t)row), "l"(l2_keep) : "memory");
+                        asm volatile("st.global.L2::cache_hint.v2.f64 [%0], {%1, %2}, %3;" ::"l"(data + pos), "d"(vr[r]), "d"(vi[r]), "l"(l2_keep) : "memory");
+#else
                         indices[pos] = (I)(col ^ (uint64_t)x);
                         data[pos] = make_double2(vr[r], vi[r]);
+#endif
                     }
                     vr[r] = 0.0;
                     vi[r] = 0.0;
