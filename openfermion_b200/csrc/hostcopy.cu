@@ -14,7 +14,6 @@
 #include <cstring>
 #include <mutex>
 #include <thread>
-#include <vector>
 
 #include "ofb_internal.cuh"
 
@@ -75,7 +74,8 @@ int staged_copy(void *d, void *h, size_t bytes, bool to_device, int device, int 
     std::lock_guard<std::mutex> lock(g_copy_mu);
     const int T = worker_count(bytes, threads);
     const size_t n_chunks = (bytes + STAGE_BYTES - 1) / STAGE_BYTES;
-    std::vector<cudaError_t> status((size_t)T, cudaSuccess);
+    cudaError_t status[MAX_WORKERS];
+    for (int t = 0; t < MAX_WORKERS; ++t) status[t] = cudaSuccess;
     auto run = [&](int t) {
         Worker &w = g_workers[t];
         cudaError_t e = worker_ready(w, device);
@@ -127,13 +127,21 @@ int staged_copy(void *d, void *h, size_t bytes, bool to_device, int device, int 
     if (T == 1) {
         run(0);
     } else {
-        std::vector<std::thread> pool;
-        pool.reserve((size_t)T);
-        for (int t = 0; t < T; ++t) pool.emplace_back(run, t);
-        for (auto &th : pool) th.join();
+        // No exception may leave this function (it is called from extern "C" entry points): a
+        // worker whose thread cannot be created runs inline in the calling thread instead.
+        std::thread pool[MAX_WORKERS];
+        for (int t = 0; t < T; ++t) {
+            try {
+                pool[t] = std::thread(run, t);
+            } catch (...) {
+                run(t);
+            }
+        }
+        for (int t = 0; t < T; ++t)
+            if (pool[t].joinable()) pool[t].join();
     }
-    for (cudaError_t e : status)
-        if (e != cudaSuccess) return cuda_fail(e, "staged host/device copy", __FILE__, __LINE__);
+    for (int t = 0; t < T; ++t)
+        if (status[t] != cudaSuccess) return cuda_fail(status[t], "staged host/device copy", __FILE__, __LINE__);
     return OFB_OK;
 }
 
