@@ -121,6 +121,84 @@ def compile_fermion_terms(terms, n_qubits):
             numpy.array(cs, dtype=numpy.complex128))
 
 
+def _parity_u64(values):
+    """parity of the set bits of a uint64 array (portable: no numpy.bitwise_count)."""
+    v = values.copy()
+    for shift in (32, 16, 8, 4, 2, 1):
+        v ^= v >> numpy.uint64(shift)
+    return (v & numpy.uint64(1)).astype(bool)
+
+
+def compile_ladder_products(modes, kinds, coefficients, n_qubits):
+    """compile_fermion_terms for MANY products with the same pattern of raising / lowering
+    operators at once: modes[N, K] (mode of factor k of product i), kinds[K] (1 raising,
+    0 lowering), coefficients[N].  Same bit logic, same skip rules (zero coefficients, products
+    that vanish on every column), same output order as a loop over the N products."""
+    modes = numpy.asarray(modes, dtype=numpy.int64).reshape(len(coefficients), -1)
+    coeff = numpy.asarray(coefficients, dtype=numpy.complex128)
+    if modes.size and int(modes.max()) > n_qubits - 1:
+        raise ValueError('Invalid number of qubits specified.')
+    count = len(coeff)
+    top = numpy.uint64(max(n_qubits - 1, 0))  # unused when there are no factors (a constant)
+    full = numpy.uint64((1 << n_qubits) - 1)
+    one = numpy.uint64(1)
+    zero = numpy.zeros(count, dtype=numpy.uint64)
+    flip, z_mask, need_mask, need_val = zero.copy(), zero.copy(), zero.copy(), zero.copy()
+    sign = numpy.zeros(count, dtype=bool)
+    dead = numpy.zeros(count, dtype=bool)
+    for k in reversed(range(modes.shape[1])):
+        bit = one << (top - modes[:, k].astype(numpy.uint64))
+        above = full ^ ((bit << one) - one)
+        want_col = numpy.full(count, not kinds[k]) ^ ((flip & bit) != 0)
+        has = (need_mask & bit) != 0
+        dead |= has & (((need_val & bit) != 0) != want_col)
+        fresh = ~has
+        need_mask |= numpy.where(fresh, bit, zero)
+        need_val |= numpy.where(fresh & want_col, bit, zero)
+        z_mask ^= above
+        sign ^= _parity_u64(flip & above)
+        flip ^= bit
+    keep = ~dead & (coeff != 0)
+    signed = numpy.where(sign, -coeff, coeff)
+    return need_mask[keep], need_val[keep], flip[keep], z_mask[keep], signed[keep]
+
+
+def compile_interaction_tensors(n_body_tensors, n_qubits, tolerance):
+    """Projected rows of constant + sum_pq h_pq p^ q + sum_pqrs g_pqrs p^ q^ r s straight from
+    the tensors, identical to compile_fermion_terms(get_fermion_operator(tensors).terms): the
+    reference's conversion (transforms/opconversions/conversions.py:117-121) visits the constant,
+    then each tensor's non-zero entries in index-product order and drops what `+=` drops
+    (|coefficient| < EQ_TOLERANCE).  n_qubits None: 1 + the highest mode of a surviving term, as
+    count_qubits of that FermionOperator.  Returns (n_qubits, rows) or None for tensors of
+    another shape."""
+    keys = set(n_body_tensors.keys())
+    if not keys <= {(), (1, 0), (1, 1, 0, 0)}:
+        return None
+    blocks = []  # (modes[N, K], kinds, coefficients[N])
+    constant = n_body_tensors.get((), 0.0)
+    if constant and abs(constant) >= tolerance:
+        blocks.append((numpy.zeros((1, 0), dtype=numpy.int64), (), numpy.array([constant])))
+    for key in ((1, 0), (1, 1, 0, 0)):
+        if key not in keys:
+            continue
+        tensor = numpy.asarray(n_body_tensors[key])
+        index = numpy.nonzero(tensor)  # C order = itertools.product order
+        values = tensor[index]
+        big = numpy.abs(values) >= tolerance
+        if numpy.any(big):
+            blocks.append((numpy.stack([axis[big] for axis in index], axis=1), key, values[big]))
+    needed = max([int(modes.max()) + 1 for modes, _, _ in blocks if modes.size], default=0)
+    if n_qubits is None:
+        n_qubits = needed
+    elif needed > n_qubits:
+        raise ValueError('Invalid number of qubits specified.')
+    parts = [compile_ladder_products(modes, kinds, values, n_qubits) for modes, kinds, values in blocks]
+    if not parts:
+        empty = numpy.zeros(0, dtype=numpy.uint64)
+        return n_qubits, (empty, empty.copy(), empty.copy(), empty.copy(), numpy.zeros(0, dtype=numpy.complex128))
+    return n_qubits, tuple(numpy.concatenate([part[k] for part in parts]) for k in range(5))
+
+
 def resolve_n_qubits(operator, n_qubits, message='Invalid number of qubits specified.'):
     needed = count_qubits(operator)
     if n_qubits is None:

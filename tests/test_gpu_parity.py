@@ -189,11 +189,16 @@ def test_golden_csc_fermion_route(case):
     assert mat.has_canonical_format
 
 
-def test_lih_sparse_operator_matches_reference():
+def test_lih_sparse_operator_matches_reference(monkeypatch):
     data = helpers.golden('lih_sto3g.npz')
     ham = hamiltonians.molecular_hamiltonian(float(data['nuclear_repulsion']), data['one_body_integrals'],
                                        data['two_body_integrals'])
-    mat = get_sparse_operator(ham)
+    mat = get_sparse_operator(ham)  # rows built array-wise from the tensors
+    monkeypatch.setenv('OFB_TENSOR_ROWS', '0')
+    via_terms = get_sparse_operator(ham)  # through the FermionOperator, as the reference converts
+    monkeypatch.delenv('OFB_TENSOR_ROWS')
+    assert numpy.array_equal(mat.indptr, via_terms.indptr) and numpy.array_equal(mat.indices, via_terms.indices)
+    assert mat.data.tobytes() == via_terms.data.tobytes()
     assert mat.nnz == int(data['nnz']) and str(mat.indices.dtype) == str(data['indices_dtype'])
     assert numpy.array_equal(mat.indptr, data['indptr'])
     assert hashlib.sha256(mat.indices.tobytes()).hexdigest() == str(data['indices_sha256'])
