@@ -33,8 +33,11 @@ def main():
     ap.add_argument('--eps', type=float, default=1e-6)
     ap.add_argument('--max-iterations', type=int, default=400)
     ap.add_argument('--skip-sector', action='store_true')
+    ap.add_argument('--native', action='store_true',
+                    help='no INFO logging: the solver runs behind the C ABI (ofb_davidson_lowest_n)')
     args = ap.parse_args()
-    logging.basicConfig(level=logging.INFO, format='%(message)s', stream=sys.stderr)
+    if not args.native:  # the reference's per-iteration log line needs the host-driven loop
+        logging.basicConfig(level=logging.INFO, format='%(message)s', stream=sys.stderr)
     _lib.require_device()
     n = args.qubits
     op = hamiltonians.molecular_jw(n // 2, seed=1234)
@@ -58,6 +61,8 @@ def main():
     out['davidson_s'] = time.perf_counter() - t0
     out['success'] = bool(success)
     out['eigenvalue'] = float(values[0])
+    out['solver'] = 'ofb_davidson_lowest_n' if args.native else 'host-driven loop'
+    out['iterations'] = getattr(dav, 'last_iterations', None)
     out['kernel_launches'] = _lib.launch_count() - launches
     vec = vectors[:, 0]
     out['norm'] = float(numpy.linalg.norm(vec))
